@@ -1,0 +1,71 @@
+"""The oracle (oracle/ref_port.py + oracle/greedy_nms.c) against the golden vectors that
+oracle/gen_golden.py produced by executing the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_manifest, golden_names, load_golden, split_rows
+from cerberusdet_b200.synth import STRIDES
+from oracle import ref_port as rp
+
+
+@pytest.mark.parametrize("name", golden_names("decode"))
+def test_decode_port_bit_exact(name):
+    g = load_golden(name)
+    nc = golden_manifest()[name]["nc"]
+    levels = [torch.from_numpy(g[f"level{i}"]) for i in range(3)]
+    y = rp.decode_port(levels, nc, STRIDES)
+    ref = torch.from_numpy(g["y"])
+    assert y.dtype == ref.dtype and y.shape == ref.shape
+    assert torch.equal(y, ref)  # same ATen kernels -> bit exact on CPU
+
+
+@pytest.mark.parametrize("greedy", ["torchvision", "c"])
+@pytest.mark.parametrize("name", golden_names("nms"))
+def test_nms_port_bit_exact(name, greedy):
+    g = load_golden(name)
+    kw = dict(golden_manifest()[name]["kwargs"])
+    pred = torch.from_numpy(g["pred"])
+    want = split_rows(g["rows"], g["counts"])
+    got = rp.nms_port(pred, greedy=greedy, **kw)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.dtype == torch.float32 and a.shape == b.shape
+        assert torch.equal(a, b)
+
+
+def test_greedy_c_matches_torchvision_random():
+    import torchvision
+
+    gen = torch.Generator().manual_seed(5)
+    for n in (0, 1, 2, 65, 700, 3000):
+        c = torch.rand(n, 2, generator=gen) * 200
+        wh = torch.rand(n, 2, generator=gen) * 60
+        boxes = torch.cat((c - wh / 2, c + wh / 2), 1)
+        boxes[n // 2 :] = boxes[n // 2 :].round()  # integer boxes: many exact-equality IoUs
+        scores = torch.rand(n, generator=gen).sort(descending=True).values
+        for thr in (0.0, 0.1, 0.45, 0.5, 0.6, 0.7, 1.0):
+            assert torch.equal(torchvision.ops.nms(boxes, scores, thr), rp.greedy_nms_c(boxes, thr))
+
+
+def test_threshold_rounding_rules():
+    # conf threshold is compared in the tensor dtype (utils/general.py:411)
+    h = torch.tensor([0.30005], dtype=torch.float16)
+    pred = torch.zeros(1, 5, 1, dtype=torch.float16)
+    pred[0, :4, 0] = torch.tensor([10, 10, 4, 4], dtype=torch.float16)
+    pred[0, 4, 0] = h
+    assert rp.nms_port(pred, conf_thres=0.3)[0].shape[0] == 0  # half(0.3) == 0.30005, not >
+    f = torch.tensor(np.float32(0.3))
+    pred32 = pred.float()
+    pred32[0, 4, 0] = f
+    assert rp.nms_port(pred32, conf_thres=0.3)[0].shape[0] == 0
+    pred32[0, 4, 0] = torch.tensor(np.nextafter(np.float32(0.3), np.float32(1)))
+    assert rp.nms_port(pred32, conf_thres=0.3)[0].shape[0] == 1
+
+
+def test_asserts_like_reference():
+    pred = torch.zeros(1, 6, 4)
+    with pytest.raises(AssertionError):
+        rp.nms_port(pred, conf_thres=1.5)
+    with pytest.raises(AssertionError):
+        rp.nms_port(pred, iou_thres=-0.1)
