@@ -1,0 +1,87 @@
+"""ctypes binding of ``libcerb_post.so`` (C ABI in ``include/cerb_post.h``).
+
+The library is the product: if it is missing or fails to load, importing the ops
+raises -- there is no CPU or eager-PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcerb_post.so")
+
+CERB_F16, CERB_F32 = 0, 1
+CERB_EINVAL, CERB_ECUDA, CERB_ENOSPC = -1, -2, -3
+
+EXPORTS = (
+    "cerb_version",
+    "cerb_last_error",
+    "cerb_decode",
+    "cerb_nms_workspace_bytes",
+    "cerb_nms",
+    "cerb_debug_set_chunking",
+)
+
+_lib = None
+
+
+class CerbLibraryError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CerbLibraryError(
+            f"{LIB_PATH} not found: build it with `sh cerberusdet_b200/csrc/build.sh` "
+            "(or __graft_entry__.build()).  cerberusdet_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ip, i, d, sz = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+    vpp = ctypes.POINTER(ctypes.c_void_p)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.cerb_version.restype = i
+    lib.cerb_version.argtypes = []
+    lib.cerb_last_error.restype = ctypes.c_char_p
+    lib.cerb_last_error.argtypes = []
+    lib.cerb_decode.restype = i
+    lib.cerb_decode.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vp]
+    lib.cerb_nms_workspace_bytes.restype = sz
+    lib.cerb_nms_workspace_bytes.argtypes = [i, i, i]
+    lib.cerb_nms.restype = i
+    lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
+    lib.cerb_debug_set_chunking.restype = i
+    lib.cerb_debug_set_chunking.argtypes = [i, i]
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().cerb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Map a C return code to the exception type the reference would raise."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == CERB_EINVAL and msg.startswith("Invalid"):
+        raise AssertionError(msg)  # reference: `assert 0 <= conf_thres <= 1` (utils/general.py:399-400)
+    if rc == CERB_EINVAL:
+        raise ValueError(msg)
+    raise CerbLibraryError(f"libcerb_post error {rc}: {msg}")
+
+
+def int_array(values):
+    return (ctypes.c_int * max(len(values), 1))(*values)
+
+
+def float_array(values):
+    return (ctypes.c_float * max(len(values), 1))(*values)
+
+
+def ptr_array(values):
+    return (ctypes.c_void_p * max(len(values), 1))(*values)

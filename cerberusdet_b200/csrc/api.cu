@@ -1,0 +1,171 @@
+// C ABI of libcerb_post.so (declared in include/cerb_post.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cerb_post.h"
+#include "cerb_kernels.h"
+
+static thread_local char g_err[512] = "";
+static int g_chunk_cap = 0, g_chunk_first = 0;
+
+void cerb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define REQUIRE(cond, ...)            \
+    do {                              \
+        if (!(cond)) {                \
+            cerb_set_error(__VA_ARGS__); \
+            return CERB_EINVAL;       \
+        }                             \
+    } while (0)
+
+static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+extern "C" int cerb_version(void) { return 100; }
+extern "C" const char* cerb_last_error(void) { return g_err; }
+
+extern "C" int cerb_debug_set_chunking(int chunk_cap, int chunk_first) {
+    if (chunk_cap == 0 && chunk_first == 0) { g_chunk_cap = g_chunk_first = 0; return 0; }
+    REQUIRE(chunk_cap >= 16 && chunk_cap <= 4096, "chunk_cap must be in [16, 4096], got %d", chunk_cap);
+    REQUIRE(chunk_first >= 1, "chunk_first must be >= 1, got %d", chunk_first);
+    g_chunk_cap = chunk_cap;
+    g_chunk_first = chunk_first;
+    return 0;
+}
+
+extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
+                           const float* strides, int dtype, void* const* y, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(lvl && nc && H && W && strides && y, "cerb_decode: null argument");
+    REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_decode: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
+    REQUIRE(L >= 1 && L <= CERB_MAX_LEVELS, "cerb_decode: L=%d outside [1, %d]", L, CERB_MAX_LEVELS);
+    REQUIRE(B >= 0, "cerb_decode: negative batch");
+    REQUIRE(dtype == CERB_F16 || dtype == CERB_F32, "cerb_decode: unsupported dtype %d", dtype);
+    DecodeParams P;
+    memset(&P, 0, sizeof(P));
+    P.T = T; P.L = L; P.B = B; P.nrows = T * L;
+    const size_t elt = dtype == CERB_F16 ? 2 : 4;
+    int vec = (int)(16 / elt);
+    long A = 0;
+    for (int l = 0; l < L; ++l) {
+        REQUIRE(H[l] > 0 && W[l] > 0, "cerb_decode: level %d has empty shape %dx%d", l, H[l], W[l]);
+        const long hw = (long)H[l] * W[l];
+        REQUIRE(hw < (1l << 30), "cerb_decode: level %d too large", l);
+        P.hw[l] = (int)hw; P.w[l] = W[l]; P.aoff[l] = (int)A; P.stride[l] = strides[l];
+        A += hw;
+        while (vec > 1 && hw % vec) vec >>= 1;
+    }
+    REQUIRE(A < (1l << 30), "cerb_decode: too many anchors");
+    P.A = (int)A;
+    for (int t = 0; t < T; ++t) {
+        REQUIRE(nc[t] >= 1, "cerb_decode: task %d has nc=%d", t, nc[t]);
+        P.nc[t] = nc[t];
+        REQUIRE(y[t] != nullptr || B == 0, "cerb_decode: y[%d] is null", t);
+        P.y[t] = y[t];
+        while (vec > 1 && !aligned_to(y[t], vec * elt)) vec >>= 1;
+        for (int l = 0; l < L; ++l) {
+            const void* p = lvl[t * L + l];
+            REQUIRE(p != nullptr || B == 0, "cerb_decode: lvl[%d][%d] is null", t, l);
+            P.lvl[t][l] = p;
+            while (vec > 1 && !aligned_to(p, vec * elt)) vec >>= 1;
+        }
+    }
+    if (B == 0) return 0;
+    cudaError_t e = cerb_launch_decode(P, dtype, vec, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_decode: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}
+
+extern "C" size_t cerb_nms_workspace_bytes(int T, int B, int max_det) {
+    if (T <= 0 || B <= 0 || max_det <= 0) return 0;
+    return cerb_nms_kept_ws_bytes(T, B, max_det);
+}
+
+// torch compares a half tensor with a Python scalar after casting the scalar to half
+// (double -> float -> half), a float tensor after casting it to float (general.py:411).
+static float round_conf_to_dtype(double conf, int dtype) {
+    float f = (float)conf;
+    if (dtype == CERB_F16) f = __half2float(__float2half_rn(f));
+    return f;
+}
+// torchvision's CPU kernel widens the fp32 quotient and compares with the double threshold:
+// (double)q > thr  <=>  q > (largest float <= thr).
+static float iou_threshold_as_float(double thr) {
+    float f = (float)thr;
+    if ((double)f > thr) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+                        double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
+                        int max_det, int max_nms, double max_wh, float* dets, int* counts, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(pred && nc, "cerb_nms: null argument");
+    REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_nms: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
+    REQUIRE(B >= 0 && A >= 0, "cerb_nms: negative size");
+    REQUIRE(dtype == CERB_F16 || dtype == CERB_F32, "cerb_nms: unsupported dtype %d", dtype);
+    REQUIRE(conf_thres >= 0.0 && conf_thres <= 1.0, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", conf_thres);
+    REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, "Invalid IoU %g, valid values are between 0.0 and 1.0", iou_thres);
+    REQUIRE(max_det >= 0 && max_nms >= 0, "cerb_nms: negative max_det/max_nms");
+    if (B == 0) return 0;
+    REQUIRE(counts != nullptr, "cerb_nms: counts is null");
+    REQUIRE(dets != nullptr || max_det == 0, "cerb_nms: dets is null");
+    NmsParams P;
+    memset(&P, 0, sizeof(P));
+    P.T = T; P.B = B; P.A = A;
+    for (int t = 0; t < T; ++t) {
+        REQUIRE(nc[t] >= 1, "cerb_nms: task %d has nc=%d", t, nc[t]);
+        REQUIRE((double)A * nc[t] < 4294967295.0, "cerb_nms: A*nc overflows the 32-bit candidate index");
+        REQUIRE(pred[t] != nullptr || A == 0, "cerb_nms: pred[%d] is null", t);
+        P.pred[t] = pred[t];
+        P.nc[t] = nc[t];
+    }
+    if (classes != nullptr && n_classes >= 0) {
+        P.use_class_filter = 1;
+        for (int i = 0; i < n_classes; ++i) {
+            const int c = classes[i];
+            if (c < 0 || c >= 32 * CERB_MAX_CLASS_WORDS) continue;  // can never match a class id
+            P.class_mask[c >> 5] |= 1u << (c & 31);
+        }
+        for (int t = 0; t < T; ++t)
+            REQUIRE(nc[t] <= 32 * CERB_MAX_CLASS_WORDS, "cerb_nms: class filter supports nc <= %d", 32 * CERB_MAX_CLASS_WORDS);
+    }
+    P.conf_thr = round_conf_to_dtype(conf_thres, dtype);
+    P.iou_thr = iou_threshold_as_float(iou_thres);
+    P.class_gap = agnostic ? 0.f : (float)max_wh;
+    P.multi_label = multi_label ? 1 : 0;
+    P.max_det = max_det;
+    P.max_nms = max_nms;
+    P.dets = dets;
+    P.counts = counts;
+    const size_t need = cerb_nms_kept_ws_bytes(T, B, max_det);
+    if (need) {
+        if (workspace == nullptr || workspace_bytes < need) {
+            cerb_set_error("cerb_nms: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+            return CERB_ENOSPC;
+        }
+        REQUIRE(aligned_to(workspace, 16), "cerb_nms: workspace must be 16-byte aligned");
+        P.kept_ws = (float*)workspace;
+    }
+    P.chunk_cap = g_chunk_cap ? g_chunk_cap : 4096;
+    int first = g_chunk_first ? g_chunk_first : (max_det + max_det / 2 + 64);
+    if (first < 256 && !g_chunk_first) first = 256;
+    if (first > P.chunk_cap) first = P.chunk_cap;
+    P.chunk_first = first;
+    cudaError_t e = cerb_launch_nms(P, dtype, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_nms: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}

@@ -1,0 +1,42 @@
+// Kernel parameter blocks and launchers shared by decode.cu / nms.cu / api.cu.
+#pragma once
+#include "cerb_common.cuh"
+
+// ------------------------------------------------------------------ decode
+struct DecodeParams {
+    const void* lvl[CERB_MAX_TASKS][CERB_MAX_LEVELS];  // raw head tensors [B, 64+nc, H_l, W_l]
+    void* y[CERB_MAX_TASKS];                           // decoded [B, 4+nc, A]
+    int nc[CERB_MAX_TASKS];
+    int hw[CERB_MAX_LEVELS];
+    int w[CERB_MAX_LEVELS];
+    int aoff[CERB_MAX_LEVELS];  // first anchor of each level inside A
+    float stride[CERB_MAX_LEVELS];
+    int B, A, T, L;
+    int nrows;                                                  // T * L
+    int row_start[CERB_MAX_TASKS * CERB_MAX_LEVELS + 1];        // first block of each (task, level) row
+    int row_blocks_per_part[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // ceil(B * hw / VEC / threads)
+};
+cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
+
+// ------------------------------------------------------------------ select + NMS
+#define CERB_MAX_CLASS_WORDS 32  // class filter bitmask: nc <= 1024
+
+struct NmsParams {
+    const void* pred[CERB_MAX_TASKS];  // [B, 4+nc, A], dtype below
+    int nc[CERB_MAX_TASKS];
+    int T, B, A;
+    float conf_thr;   // already rounded to the prediction dtype (reference general.py:411)
+    float iou_thr;    // largest float <= the double threshold: (double)ovr > thr  <=>  ovr > iou_thr
+    float class_gap;  // max_wh (7680) or 0 when agnostic (general.py:462)
+    int multi_label;
+    int max_det, max_nms;
+    int use_class_filter;
+    unsigned class_mask[CERB_MAX_CLASS_WORDS];
+    float* dets;     // [T, B, max_det, 6]
+    int* counts;     // [T, B]
+    float* kept_ws;  // global kept-list storage [T*B, max_det, 5] when max_det is too large for smem, else null
+    int chunk_cap;   // candidates sorted per chunk (<= NMS_CAP); tests shrink it to force the rare paths
+    int chunk_first; // size target of the first chunk
+};
+cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
+size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);

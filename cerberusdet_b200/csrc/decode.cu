@@ -1,0 +1,200 @@
+// Fused Detect-head decode for every task head in ONE launch.
+//
+// Replaces the eval branch of the reference Detect.forward after the conv towers
+// (reference models/yolo.py:93-99): make_anchors (utils/tal.py:181-193), the
+// [B,no,A] concat/split (yolo.py:97), DFL softmax-expectation (yolo.py:57-59),
+// dist2bbox(xywh) (utils/tal.py:196-205), * stride (yolo.py:98) and the class
+// sigmoid + concat (yolo.py:99).  ~15 ATen launches and ~4.5x the algorithmic HBM
+// traffic there; here each raw element is read once and each y element written once.
+//
+// Work decomposition.  A "row" is one (task, level).  Inside a row the blocks are laid
+// out as [part][vector-block]: part 0 owns DFL sides l,r -> (cx, w); part 1 owns sides
+// t,b -> (cy, h); parts 2.. own chunks of CLS_CHUNK class channels.  A thread owns VEC
+// consecutive anchors of one image (one 128-bit access per channel), so a warp reads
+// 512 contiguous bytes per channel.  Anchors are computed analytically.
+#include "cerb_kernels.h"
+
+#define DEC_THREADS 128
+#define CLS_CHUNK 32
+#define LOG2E_F 1.4426950408889634f
+
+template <int BYTES> struct RawOf;
+template <> struct RawOf<16> { typedef uint4 type; };
+template <> struct RawOf<8> { typedef uint2 type; };
+template <> struct RawOf<4> { typedef uint32_t type; };
+template <> struct RawOf<2> { typedef uint16_t type; };
+
+template <typename T, int VEC> union Pack {
+    typename RawOf<sizeof(T) * VEC>::type raw;
+    T e[VEC];
+};
+
+template <typename T, int VEC> __device__ __forceinline__ Pack<T, VEC> load_pack(const T* p) {
+    Pack<T, VEC> r;
+    if constexpr (sizeof(T) * VEC == 16) {
+        r.raw = ldg_stream16(p);
+    } else {
+        r.raw = __ldg(reinterpret_cast<const typename RawOf<sizeof(T) * VEC>::type*>(p));
+    }
+    return r;
+}
+template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& v) {
+    if constexpr (sizeof(T) * VEC == 16) {
+        stg_stream16(p, v.raw);
+    } else {
+        *reinterpret_cast<typename RawOf<sizeof(T) * VEC>::type*>(p) = v.raw;
+    }
+}
+
+// Expected DFL distance of one box side for VEC anchors: sum_k k * softmax(logits)_k.
+// Rounding points follow the reference for half tensors: probabilities are rounded to
+// half (softmax output), the 1x1 conv accumulates in fp32 and rounds once.
+template <typename T, int VEC>
+__device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw, float (&d)[VEC]) {
+    Pack<T, VEC> v[CERB_REG_MAX];
+#pragma unroll
+    for (int k = 0; k < CERB_REG_MAX; ++k) v[k] = load_pack<T, VEC>(side_base + (size_t)k * hw);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float x[CERB_REG_MAX];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < CERB_REG_MAX; ++k) {
+            x[k] = to_f32<T>(v[k].e[i]);
+            m = fmaxf(m, x[k]);
+        }
+        const float mb = m * LOG2E_F;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < CERB_REG_MAX; ++k) {
+            x[k] = fast_ex2(fmaf(x[k], LOG2E_F, -mb));
+            s += x[k];
+        }
+        const float inv = fast_rcp(s);
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 1; k < CERB_REG_MAX; ++k) acc = fmaf((float)k, rnd<T>(x[k] * inv), acc);
+        d[i] = rnd<T>(acc);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_constant__ DecodeParams P) {
+    // ---- block -> (row, part, vector block); uniform per block
+    int row = 0;
+    {
+        int lo = 0, hi = P.nrows;  // row_start[lo] <= blockIdx.x < row_start[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((int)blockIdx.x >= P.row_start[mid]) lo = mid; else hi = mid;
+        }
+        row = lo;
+    }
+    const int task = row / P.L, level = row - task * P.L;
+    const int in_row = blockIdx.x - P.row_start[row];
+    const int bpp = P.row_blocks_per_part[row];
+    const int part = in_row / bpp;
+    const int vblk = in_row - part * bpp;
+
+    const int hw = P.hw[level];
+    const int nvec = hw / VEC;
+    const int item = vblk * DEC_THREADS + threadIdx.x;
+    if (item >= P.B * nvec) return;
+    const int b = item / nvec;
+    const int a0 = (item - b * nvec) * VEC;  // first anchor inside the level
+
+    const int nc = P.nc[task];
+    const int no = 4 * CERB_REG_MAX + nc;
+    const T* __restrict__ in = reinterpret_cast<const T*>(P.lvl[task][level]) + (size_t)b * no * hw + a0;
+    T* __restrict__ out = reinterpret_cast<T*>(P.y[task]) + (size_t)b * (4 + nc) * P.A + P.aoff[level] + a0;
+
+    if (part < 2) {
+        // sides (l, r) -> cx, w   or   (t, b) -> cy, h      (utils/tal.py:198-204)
+        float dlo[VEC], dhi[VEC];
+        dfl_side<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, dlo);
+        dfl_side<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, dhi);
+        const int W = P.w[level];
+        const float st = P.stride[level];
+        Pack<T, VEC> oc, os;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int a = a0 + i;
+            const int g = (part == 0) ? (a % W) : (a / W);
+            const float ac = rnd<T>(rnd<T>((float)g) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
+            const float p1 = rnd<T>(ac - dlo[i]);
+            const float p2 = rnd<T>(ac + dhi[i]);
+            const float c = rnd<T>(rnd<T>(p1 + p2) * 0.5f);
+            const float sz = rnd<T>(p2 - p1);
+            oc.e[i] = from_f32<T>(c * st);
+            os.e[i] = from_f32<T>(sz * st);
+        }
+        store_pack<T, VEC>(out + (size_t)part * P.A, oc);
+        store_pack<T, VEC>(out + (size_t)(part + 2) * P.A, os);
+    } else {
+        // class scores: sigmoid (yolo.py:99)
+        const int c0 = (part - 2) * CLS_CHUNK;
+        const int c1 = min(nc, c0 + CLS_CHUNK);
+        const T* __restrict__ cin = in + (size_t)(4 * CERB_REG_MAX) * hw;
+        T* __restrict__ cout = out + (size_t)4 * P.A;
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
+            Pack<T, VEC> v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float x = to_f32<T>(v[u].e[i]);
+                    v[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                }
+                store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, v[u]);
+            }
+        }
+        for (; c < c1; ++c) {
+            Pack<T, VEC> v = load_pack<T, VEC>(cin + (size_t)c * hw);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float x = to_f32<T>(v.e[i]);
+                v.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+            }
+            store_pack<T, VEC>(cout + (size_t)c * P.A, v);
+        }
+    }
+}
+
+template <typename T, int VEC> static cudaError_t launch_decode_t(DecodeParams& P, cudaStream_t stream) {
+    int blocks = 0;
+    for (int t = 0; t < P.T; ++t)
+        for (int l = 0; l < P.L; ++l) {
+            const int row = t * P.L + l;
+            const long items = (long)P.B * (P.hw[l] / VEC);
+            const int bpp = (int)((items + DEC_THREADS - 1) / DEC_THREADS);
+            const int parts = 2 + (P.nc[t] + CLS_CHUNK - 1) / CLS_CHUNK;
+            P.row_start[row] = blocks;
+            P.row_blocks_per_part[row] = bpp > 0 ? bpp : 1;
+            blocks += bpp * parts;
+        }
+    P.row_start[P.nrows] = blocks;
+    if (blocks == 0) return cudaSuccess;
+    decode_kernel<T, VEC><<<blocks, DEC_THREADS, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+// vec = anchors per thread the caller proved legal (alignment + divisibility)
+cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream) {
+    if (dtype == CERB_DTYPE_F16) {
+        switch (vec) {
+            case 8: return launch_decode_t<__half, 8>(P, stream);
+            case 4: return launch_decode_t<__half, 4>(P, stream);
+            case 2: return launch_decode_t<__half, 2>(P, stream);
+            default: return launch_decode_t<__half, 1>(P, stream);
+        }
+    } else {
+        switch (vec) {
+            case 4: return launch_decode_t<float, 4>(P, stream);
+            case 2: return launch_decode_t<float, 2>(P, stream);
+            default: return launch_decode_t<float, 1>(P, stream);
+        }
+    }
+}

@@ -1,0 +1,428 @@
+// Per-task confidence filter, candidate expansion, lazy top-k ordering and class-offset
+// greedy NMS -- one CTA per (task, image) segment, all segments in ONE launch.
+//
+// Replaces reference non_max_suppression (utils/general.py:360-481) incl. xywh2xyxy
+// (:272-288) and the third-party torchvision.ops.nms it calls (:464).  The reference
+// runs ~25 ATen launches and ~4 host syncs per (image, task) and materialises every
+// candidate; this kernel never materialises the candidate table:
+//
+//  * Candidates are implicit: (anchor a, class c) pairs of the prediction whose score
+//    passes the threshold (multi-label, :444-446) or the best class of an anchor
+//    (:447-449).  Each gets a unique 64-bit key  score_bits << 32 | ~(a*nc + c), so that
+//    descending key order == "score descending, candidate index ascending", the
+//    canonical form of the reference's sort at :459 (ties there are unspecified).
+//  * Greedy NMS is order-causal and stops at max_det (:465), so only a prefix of the
+//    sorted order is ever needed.  A 4096-bin histogram of the top 12 key bits (one pass
+//    over the scores, in shared memory) locates successive chunks of <= CAP keys; each
+//    chunk is gathered, bitonic-sorted in shared memory and consumed; the kernel stops
+//    as soon as max_det boxes are kept or max_nms candidates (:459) were consumed.
+//    A bin that alone exceeds CAP (massive ties) is refined by deeper radix levels.
+//  * Suppression (:462-465): candidates are taken in tiles of 256; a tile is first
+//    tested against the kept list (shared memory), then resolved internally with a
+//    256x256 IoU bitmask and a ballot sweep by one warp.  IoU arithmetic reproduces
+//    torchvision's CPU kernel: separately rounded fp32 ops on class-offset boxes, strict
+//    '>' against the threshold (the double-precision compare is folded into iou_thr).
+#include "cerb_kernels.h"
+
+#define NMS_THREADS 512
+#define NMS_TILE 256
+#define NMS_TILE_WORDS (NMS_TILE / 64)
+#define NMS_CAP 4096         // max keys sorted at once
+#define NMS_BINS 4096        // 12-bit radix digits
+#define NMS_KEPT_SMEM 1024   // kept list lives in smem up to this max_det
+
+typedef unsigned long long u64;
+
+struct __align__(16) NmsSmem {
+    unsigned g0[NMS_BINS + 8];   // level-0: G0[d] = #keys with digit >= d ; G0[4096] = 0
+    unsigned g1[NMS_BINS + 8];   // scratch for deeper levels
+    u64 keys[NMS_CAP];
+    float4 tbox[NMS_TILE];       // class-offset corners of the tile's candidates
+    float4 traw[NMS_TILE];       // un-offset corners (output)
+    float tarea[NMS_TILE];
+    float tscore[NMS_TILE];
+    int tcls[NMS_TILE];
+    u64 mask[NMS_TILE][NMS_TILE_WORDS];
+    u64 keepmask[NMS_TILE_WORDS];
+    unsigned alive32[NMS_TILE / 32];
+    unsigned char tdead[NMS_TILE];
+    unsigned warp_tot[NMS_THREADS / 32];
+    unsigned counter;
+    float4 kbox[NMS_KEPT_SMEM];
+    float karea[NMS_KEPT_SMEM];
+};
+
+// ---- IoU test exactly as torchvision's CPU kernel does it (std::max/std::min semantics,
+// one rounding per operation, no FMA).  box i is the earlier (kept) box.
+__device__ __forceinline__ bool suppresses(const float4 bi, const float ai, const float4 bj, const float aj,
+                                           const float thr) {
+    const float xx1 = (bi.x < bj.x) ? bj.x : bi.x;
+    const float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
+    const float xx2 = (bj.z < bi.z) ? bj.z : bi.z;
+    const float yy2 = (bj.w < bi.w) ? bj.w : bi.w;
+    const float dw = __fsub_rn(xx2, xx1), dh = __fsub_rn(yy2, yy1);
+    const float w = (0.f < dw) ? dw : 0.f;
+    const float h = (0.f < dh) ? dh : 0.f;
+    const float inter = __fmul_rn(w, h);
+    if (!(inter > 0.f)) return false;  // quotient would be 0 (or NaN): never > thr >= 0
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    return __fdiv_rn(inter, uni) > thr;
+}
+
+// ---- enumerate the candidate keys of one segment; f(key) is called once per candidate.
+template <typename T, bool MULTI, typename F>
+__device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, int nc, int A, float thr,
+                                                   const NmsParams& P, F f) {
+    const T* __restrict__ sc = img + (size_t)4 * A;
+    if (MULTI) {
+        for (int c = 0; c < nc; ++c) {
+            if (P.use_class_filter && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
+            const T* __restrict__ row = sc + (size_t)c * A;
+            for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
+                const float s = to_f32<T>(__ldg(row + a));
+                if (s > thr) f(((u64)__float_as_uint(s) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(a * nc + c)));
+            }
+        }
+    } else {
+        for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
+            float best = to_f32<T>(__ldg(sc + a));
+            int bc = 0;
+            for (int c = 1; c < nc; ++c) {
+                const float s = to_f32<T>(__ldg(sc + (size_t)c * A + a));
+                if (s > best) { best = s; bc = c; }  // lowest index wins ties (torch.max)
+            }
+            if (best > thr) {
+                if (P.use_class_filter && !((P.class_mask[bc >> 5] >> (bc & 31)) & 1u)) continue;
+                f(((u64)__float_as_uint(best) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(a * nc + bc)));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int level_shift(int lvl) { return lvl < 5 ? 52 - 12 * lvl : 0; }
+__device__ __forceinline__ unsigned level_digit(u64 key, int lvl) {
+    return lvl < 5 ? (unsigned)(key >> (52 - 12 * lvl)) & 0xFFFu : (unsigned)key & 0xFu;
+}
+
+// in-place: h[d] (counts) -> G[d] = sum_{d' >= d} h[d'], G[NMS_BINS] = 0.  All threads call.
+__device__ void suffix_scan(unsigned* h, unsigned* warp_tot) {
+    constexpr int PER = NMS_BINS / NMS_THREADS;  // 8
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    // thread t owns reversed positions r in [PER*t, PER*t+PER), bin = NMS_BINS-1-r
+    unsigned v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = h[NMS_BINS - 1 - (PER * t + i)]; sum += v[i]; }
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    unsigned run = base + inc - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { run += v[i]; h[NMS_BINS - 1 - (PER * t + i)] = run; }
+    if (t == 0) h[NMS_BINS] = 0;
+    __syncthreads();
+}
+
+// largest digit d in [0, hi) with G[d] - base >= need   (G non-increasing in d; caller guarantees G[0]-base >= need)
+__device__ __forceinline__ int find_digit(const unsigned* G, int hi, unsigned base, unsigned need) {
+    int lo = 0, up = hi;  // invariant: G[lo]-base >= need ; (up == hi or G[up]-base < need)
+    while (up - lo > 1) {
+        const int mid = (lo + up) >> 1;
+        if (G[mid] - base >= need) lo = mid; else up = mid;
+    }
+    return lo;
+}
+
+template <typename T, bool MULTI>
+__global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_constant__ NmsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
+
+    const int seg = blockIdx.x;
+    const int task = seg / P.B, b = seg - task * P.B;
+    const int nc = P.nc[task], A = P.A;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const T* __restrict__ img = reinterpret_cast<const T*>(P.pred[task]) + (size_t)b * (4 + nc) * A;
+    float* __restrict__ dets = P.dets + (size_t)seg * P.max_det * 6;
+    const float thr = P.conf_thr, iou_thr = P.iou_thr;
+    const int max_det = P.max_det;
+    const unsigned cap = (unsigned)P.chunk_cap;
+
+    float4* kbox = S.kbox;
+    float* karea = S.karea;
+    if (max_det > NMS_KEPT_SMEM) {
+        float* ws = P.kept_ws + (size_t)seg * max_det * 5;
+        kbox = reinterpret_cast<float4*>(ws);
+        karea = ws + (size_t)max_det * 4;
+    }
+
+    // ---------------- level-0 histogram over every candidate of the segment
+    for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
+    __syncthreads();
+    for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) { atomicAdd(&S.g0[(unsigned)(key >> 52)], 1u); });
+    __syncthreads();
+    suffix_scan(S.g0, S.warp_tot);
+
+    const unsigned total = S.g0[0];
+    const unsigned limit = min(total, (unsigned)max(P.max_nms, 0));
+    unsigned consumed = 0;
+    int kept = 0;
+    unsigned target = min((unsigned)max(P.chunk_first, 1), cap);
+
+    // -------- consume the sorted chunk in S.keys[0..n) (first `take` entries) ; returns updated kept
+    auto consume_chunk = [&](unsigned n, unsigned take) {
+        // bitonic sort, descending, padded with zeros (keys are never 0)
+        unsigned n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (unsigned i = n + tid; i < n2; i += NMS_THREADS) S.keys[i] = 0ull;
+        __syncthreads();
+        for (unsigned k = 2; k <= n2; k <<= 1) {
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned i = tid; i < n2; i += NMS_THREADS) {
+                    const unsigned ixj = i ^ j;
+                    if (ixj > i) {
+                        const u64 x = S.keys[i], y = S.keys[ixj];
+                        const bool desc = ((i & k) == 0);
+                        if (desc ? (x < y) : (x > y)) { S.keys[i] = y; S.keys[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // tiles
+        for (unsigned t0 = 0; t0 < take && kept < max_det; t0 += NMS_TILE) {
+            const int nt = (int)min((unsigned)NMS_TILE, take - t0);
+            // A: materialise the tile's boxes  (general.py:443 xywh2xyxy in dtype, :462-463 class offset in fp32)
+            if (tid < NMS_TILE) {
+                unsigned char dead = 1;
+                if (tid < nt) {
+                    const u64 key = S.keys[t0 + tid];
+                    const unsigned idx = 0xFFFFFFFFu - (unsigned)key;
+                    const int a = idx / nc, c = idx - a * nc;
+                    const float cx = to_f32<T>(__ldg(img + a));
+                    const float cy = to_f32<T>(__ldg(img + (size_t)A + a));
+                    const float bw = to_f32<T>(__ldg(img + (size_t)2 * A + a));
+                    const float bh = to_f32<T>(__ldg(img + (size_t)3 * A + a));
+                    const float hw_ = rnd<T>(bw * 0.5f), hh_ = rnd<T>(bh * 0.5f);
+                    float4 r;
+                    r.x = rnd<T>(__fsub_rn(cx, hw_));
+                    r.y = rnd<T>(__fsub_rn(cy, hh_));
+                    r.z = rnd<T>(__fadd_rn(cx, hw_));
+                    r.w = rnd<T>(__fadd_rn(cy, hh_));
+                    const float off = __fmul_rn((float)c, P.class_gap);
+                    float4 o;
+                    o.x = __fadd_rn(r.x, off);
+                    o.y = __fadd_rn(r.y, off);
+                    o.z = __fadd_rn(r.z, off);
+                    o.w = __fadd_rn(r.w, off);
+                    S.traw[tid] = r;
+                    S.tbox[tid] = o;
+                    S.tarea[tid] = __fmul_rn(__fsub_rn(o.z, o.x), __fsub_rn(o.w, o.y));
+                    S.tscore[tid] = __uint_as_float((unsigned)(key >> 32));
+                    S.tcls[tid] = c;
+                    dead = 0;
+                }
+                S.tdead[tid] = dead;
+            }
+            __syncthreads();
+            // B: against the kept list (two threads per candidate, each takes half of the list)
+            {
+                const int j = tid & (NMS_TILE - 1), half = tid >> 8;
+                if (j < nt && kept > 0) {
+                    const int mid = (kept + 1) >> 1;
+                    const int k0 = half ? mid : 0, k1 = half ? kept : mid;
+                    const float4 bj = S.tbox[j];
+                    const float aj = S.tarea[j];
+                    for (int k = k0; k < k1; ++k) {
+                        if (suppresses(kbox[k], karea[k], bj, aj, iou_thr)) { S.tdead[j] = 1; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            // C: pairwise mask inside the tile; item = (i, word)
+            if (tid < NMS_TILE) {
+                const unsigned al = __ballot_sync(0xffffffffu, S.tdead[tid] == 0);
+                if (lane == 0) S.alive32[wid] = al;
+            }
+            for (int item = tid; item < NMS_TILE * NMS_TILE_WORDS; item += NMS_THREADS) {
+                const int i = item & (NMS_TILE - 1), w = item >> 8;
+                u64 bits = 0;
+                if (i < nt && !S.tdead[i] && (w * 64 + 63) > i) {
+                    const float4 bi = S.tbox[i];
+                    const float ai = S.tarea[i];
+                    const int j0 = w * 64;
+                    const int jend = min(64, nt - j0);
+                    for (int jj = 0; jj < jend; ++jj) {
+                        const int j = j0 + jj;
+                        if (j > i && !S.tdead[j] && suppresses(bi, ai, S.tbox[j], S.tarea[j], iou_thr))
+                            bits |= 1ull << jj;
+                    }
+                }
+                S.mask[i][w] = bits;
+            }
+            __syncthreads();
+            // D: greedy sweep over the tile by warp 0 (lane l < 4 owns word l)
+            if (wid == 0) {
+                u64 alive_w = 0, rem_w = 0, keep_w = 0;
+                if (lane < NMS_TILE_WORDS)
+                    alive_w = ((u64)S.alive32[2 * lane + 1] << 32) | (u64)S.alive32[2 * lane];
+                int budget = max_det - kept;
+                while (budget > 0) {
+                    const u64 cand = alive_w & ~rem_w;
+                    const unsigned vote = __ballot_sync(0xffffffffu, cand != 0ull);
+                    if (!vote) break;
+                    const int src = __ffs(vote) - 1;
+                    const int bit = __shfl_sync(0xffffffffu, __ffsll((long long)cand) - 1, src);
+                    const int i = src * 64 + bit;
+                    if (lane == src) { keep_w |= 1ull << bit; alive_w &= ~(1ull << bit); }
+                    if (lane < NMS_TILE_WORDS) rem_w |= S.mask[i][lane];
+                    --budget;
+                }
+                if (lane < NMS_TILE_WORDS) S.keepmask[lane] = keep_w;
+            }
+            __syncthreads();
+            // E: append the kept ones (in order) to the kept list and to the output
+            int added = 0;
+#pragma unroll
+            for (int w = 0; w < NMS_TILE_WORDS; ++w) added += __popcll(S.keepmask[w]);
+            if (tid < nt) {
+                const int w = tid >> 6, bit = tid & 63;
+                if ((S.keepmask[w] >> bit) & 1ull) {
+                    int pos = kept + __popcll(S.keepmask[w] & ((1ull << bit) - 1ull));
+                    for (int ww = 0; ww < w; ++ww) pos += __popcll(S.keepmask[ww]);
+                    kbox[pos] = S.tbox[tid];
+                    karea[pos] = S.tarea[tid];
+                    const float4 r = S.traw[tid];
+                    float* o = dets + (size_t)pos * 6;  // general.py:474 rows (x1,y1,x2,y2,conf,cls)
+                    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+                    o[4] = S.tscore[tid];
+                    o[5] = (float)S.tcls[tid];
+                }
+            }
+            kept += added;
+            __syncthreads();
+        }
+    };
+
+    // -------- gather the keys in [lo, hi) into S.keys ; returns count (uniform)
+    auto collect = [&](u64 lo, u64 hi) -> unsigned {
+        if (tid == 0) S.counter = 0;
+        __syncthreads();
+        for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) {
+            if (key >= lo && key < hi) {
+                const unsigned p = atomicAdd(&S.counter, 1u);
+                if (p < NMS_CAP) S.keys[p] = key;
+            }
+        });
+        __syncthreads();
+        const unsigned n = S.counter;
+        __syncthreads();
+        return n;
+    };
+
+    // -------- a level-0 bin that alone exceeds the chunk capacity: refine by deeper digits
+    auto overflow_bin = [&](int bin) {
+        const u64 lowlim = (u64)bin << 52;
+        u64 bnd = (u64)(bin + 1) << 52;
+        while (consumed < limit && kept < max_det) {
+            u64 lo = lowlim, hi = bnd, L = lowlim;
+            int lvl = 1;
+            bool empty = false;
+            for (;;) {
+                for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g1[i] = 0;
+                __syncthreads();
+                for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) {
+                    if (key >= lo && key < hi) atomicAdd(&S.g1[level_digit(key, lvl)], 1u);
+                });
+                __syncthreads();
+                suffix_scan(S.g1, S.warp_tot);
+                const unsigned tot = S.g1[0];
+                if (tot == 0) { empty = true; break; }
+                if (tot <= cap) { L = lo; break; }
+                const unsigned need = min(cap, limit - consumed);
+                const int nb = lvl < 5 ? NMS_BINS : 16;
+                const int sh = level_shift(lvl);
+                const u64 parent = lvl < 5 ? (lo >> (sh + 12)) << (sh + 12) : (lo >> 4) << 4;
+                const int d = find_digit(S.g1, nb, 0u, min(need, tot));
+                const unsigned cnt = S.g1[d];
+                if (cnt <= cap) { L = parent | ((u64)d << sh); break; }
+                const unsigned c1 = S.g1[d + 1];
+                if (c1 > 0) { L = parent | ((u64)(d + 1) << sh); break; }
+                const u64 blo = parent | ((u64)d << sh);
+                const u64 bhi = blo + (1ull << sh);
+                lo = lo > blo ? lo : blo;
+                hi = hi < bhi ? hi : bhi;
+                ++lvl;
+                __syncthreads();
+            }
+            __syncthreads();
+            if (empty) return;
+            if (L < lowlim) L = lowlim;
+            const unsigned n = collect(L, bnd);
+            const unsigned take = min(n, limit - consumed);
+            consume_chunk(n, take);
+            consumed += take;
+            bnd = L;
+            if (L == lowlim) return;
+        }
+    };
+
+    // ---------------- main loop over level-0 digit ranges, from the top
+    int hi0 = NMS_BINS;
+    while (consumed < limit && kept < max_det && hi0 > 0) {
+        const unsigned base = S.g0[hi0];
+        if (S.g0[0] == base) break;  // nothing left below
+        const unsigned remaining = S.g0[0] - base;
+        const unsigned need = min(min(target, limit - consumed), remaining);
+        const int d = find_digit(S.g0, hi0, base, need);
+        const unsigned cnt = S.g0[d] - base;
+        int lo0 = d;
+        if (cnt > cap) {
+            const unsigned c1 = S.g0[d + 1] - base;
+            if (c1 > 0) {
+                lo0 = d + 1;
+            } else {
+                overflow_bin(d);
+                hi0 = d;
+                target = cap;
+                continue;
+            }
+        }
+        const unsigned n = collect((u64)lo0 << 52, (u64)hi0 << 52);
+        const unsigned take = min(n, limit - consumed);
+        consume_chunk(n, take);
+        consumed += take;
+        hi0 = lo0;
+        target = min(target * 2u, cap);
+    }
+
+    if (tid == 0) P.counts[seg] = kept;
+}
+
+size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
+    if (max_det <= NMS_KEPT_SMEM) return 0;
+    return (size_t)T * B * max_det * 5 * sizeof(float);
+}
+
+template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParams& P, cudaStream_t stream) {
+    const size_t smem = sizeof(NmsSmem);
+    cudaError_t e = cudaFuncSetAttribute(nms_kernel<T, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nms_kernel<T, MULTI><<<P.T * P.B, NMS_THREADS, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream) {
+    if (P.T * P.B == 0) return cudaSuccess;
+    // multi_label &= nc > 1 (general.py:419): with nc == 1 both modes select the same candidates
+    const bool multi = P.multi_label != 0;
+    if (dtype == CERB_DTYPE_F16)
+        return multi ? launch_nms_t<__half, true>(P, stream) : launch_nms_t<__half, false>(P, stream);
+    return multi ? launch_nms_t<float, true>(P, stream) : launch_nms_t<float, false>(P, stream);
+}

@@ -1,0 +1,158 @@
+"""torch custom ops ``cerb::decode`` and ``cerb::nms`` over the C ABI.
+
+PyTorch is plumbing here (device memory, streams); the arithmetic is in
+``csrc/decode.cu`` and ``csrc/nms.cu``.  Inputs must be CUDA tensors: a CPU tensor
+raises ``TypeError`` -- there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_WH = 7680.0  # reference utils/general.py:415
+MAX_NMS = 30000  # reference utils/general.py:416
+
+_DTYPES = {torch.float16: _lib.CERB_F16, torch.float32: _lib.CERB_F32}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"cerberusdet_b200 supports float16 and float32 tensors, got {t.dtype}") from None
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise TypeError(f"{what} must be a CUDA tensor (cerberusdet_b200 has no CPU path), got device {t.device}")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+@torch.library.custom_op("cerb::decode", mutates_args=())
+def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
+    lib = _lib.load()
+    T = len(nc)
+    if T == 0 or len(levels) % T:
+        raise ValueError("levels must hold T*L tensors, task-major")
+    L = len(levels) // T
+    if len(strides) != L:
+        raise ValueError(f"expected {L} strides, got {len(strides)}")
+    first = levels[0]
+    _require_cuda(first, "head tensors")
+    code = _dtype_code(first)
+    B = first.shape[0]
+    H = [int(levels[l].shape[2]) for l in range(L)]
+    W = [int(levels[l].shape[3]) for l in range(L)]
+    A = sum(h * w for h, w in zip(H, W))
+    lv = []
+    for t in range(T):
+        for l in range(L):
+            x = levels[t * L + l]
+            if x.device != first.device or x.dtype != first.dtype:
+                raise TypeError("all head tensors must share device and dtype")
+            if tuple(x.shape) != (B, 64 + nc[t], H[l], W[l]):
+                raise ValueError(f"task {t} level {l}: expected {(B, 64 + nc[t], H[l], W[l])}, got {tuple(x.shape)}")
+            lv.append(x.contiguous())
+    ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
+    with torch.cuda.device(first.device):
+        rc = lib.cerb_decode(
+            _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(list(nc)), T, L, B,
+            _lib.int_array(H), _lib.int_array(W), _lib.float_array([float(s) for s in strides]), code,
+            _lib.ptr_array([y.data_ptr() for y in ys]), _stream_ptr(first.device),
+        )
+    _lib.check(rc)
+    return ys
+
+
+@decode_op.register_fake
+def _(levels, nc, strides):
+    T = len(nc)
+    L = len(levels) // T
+    B = levels[0].shape[0]
+    A = sum(levels[l].shape[2] * levels[l].shape[3] for l in range(L))
+    return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)]
+
+
+@torch.library.custom_op("cerb::nms", mutates_args=())
+def nms_op(
+    preds: Sequence[torch.Tensor],
+    conf_thres: float,
+    iou_thres: float,
+    classes: Optional[Sequence[int]],
+    agnostic: bool,
+    multi_label: bool,
+    max_det: int,
+    max_nms: int,
+    max_wh: float,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    T = len(preds)
+    first = preds[0]
+    _require_cuda(first, "prediction")
+    code = _dtype_code(first)
+    B, A = int(first.shape[0]), int(first.shape[2])
+    ncs, ps = [], []
+    for p in preds:
+        if p.device != first.device or p.dtype != first.dtype or p.dim() != 3 or p.shape[0] != B or p.shape[2] != A:
+            raise ValueError("all predictions must be [B, 4+nc, A] on one device with one dtype")
+        ncs.append(int(p.shape[1]) - 4)
+        ps.append(p.contiguous())
+    dev = first.device
+    dets = torch.zeros((T, B, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.zeros((T, B), dtype=torch.int32, device=dev)
+    ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    cls_arr = _lib.int_array(list(classes)) if classes is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.cerb_nms(
+            _lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
+            float(conf_thres), float(iou_thres), cls_arr, len(classes) if classes is not None else 0,
+            int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh),
+            dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
+            _stream_ptr(dev),
+        )
+    _lib.check(rc)
+    return dets, counts
+
+
+@nms_op.register_fake
+def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+    T, B = len(preds), preds[0].shape[0]
+    return (preds[0].new_empty((T, B, max_det, 6), dtype=torch.float32),
+            preds[0].new_empty((T, B), dtype=torch.int32))
+
+
+# ----------------------------------------------------------------------------- friendly wrappers
+def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float]) -> List[torch.Tensor]:
+    """``task_levels[t][l]`` = raw head tensor ``[B, 64+nc_t, H_l, W_l]`` -> ``y_t [B, 4+nc_t, A]``
+    for every task in one launch (reference Detect.forward eval branch, models/yolo.py:93-99)."""
+    flat = [x for lv in task_levels for x in lv]
+    nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
+    return decode_op(flat, nc, [float(s) for s in strides])
+
+
+def nms_batched(
+    preds: Sequence[torch.Tensor],
+    conf_thres: float = 0.25,
+    iou_thres: float = 0.45,
+    classes: Optional[Sequence[int]] = None,
+    agnostic: bool = False,
+    multi_label: bool = False,
+    max_det: int = 300,
+    max_nms: int = MAX_NMS,
+    max_wh: float = MAX_WH,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All task heads, all images, one launch.  Returns padded ``dets[T,B,max_det,6]`` and
+    ``counts[T,B]`` (device tensors; no host sync)."""
+    # reference asserts (utils/general.py:399-400) -- same exception type and wording
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    return nms_op(list(preds), float(conf_thres), float(iou_thres),
+                  None if classes is None else [int(c) for c in classes],
+                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh))

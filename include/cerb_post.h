@@ -1,0 +1,99 @@
+/*
+ * cerb_post.h -- C ABI of libcerb_post.so, the B200 (sm_100a) post-head path for
+ * CerberusDet: Detect decode + per-task non_max_suppression.
+ *
+ * The reference (ai-forever/CerberusDet) is pure Python and has no FFI; its "operator
+ * interface" for this path is three Python symbols.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference root).  INTEGRATION.md
+ * shows the ctypes binding and the monkey-patch a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Pointer *arrays* (lvl, y, pred, nc, H, W, strides,
+ *    classes) are HOST arrays; what they point to (tensors, dets, counts, workspace) is
+ *    DEVICE memory owned by the caller.  The library never allocates, frees or keeps a
+ *    pointer after the call returns.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device.  Re-entrant; safe from several host threads on
+ *    different streams.
+ *  - Return 0 on success, a negative CERB_E* code otherwise; cerb_last_error() gives the
+ *    calling thread's message.  There is no CPU fallback.
+ *  - dtype: CERB_F16 (IEEE half) or CERB_F32; tensors are contiguous.
+ */
+#ifndef CERB_POST_H
+#define CERB_POST_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CERB_F16 0
+#define CERB_F32 1
+
+#define CERB_MAX_TASKS_ABI 8
+#define CERB_MAX_LEVELS_ABI 4
+
+#define CERB_EINVAL (-1)  /* bad argument (message says which) */
+#define CERB_ECUDA (-2)   /* CUDA runtime error at launch */
+#define CERB_ENOSPC (-3)  /* workspace too small */
+
+/* Library version, major*10000 + minor*100 + patch. */
+int cerb_version(void);
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* cerb_last_error(void);
+
+/*
+ * Detect-head decode for T task heads in one launch.
+ * Replaces the eval branch of Detect.forward after the conv towers
+ * (cerberusdet/models/yolo.py:93-99) together with make_anchors
+ * (cerberusdet/utils/tal.py:181-193), DFL.forward (models/yolo.py:57-59) and
+ * dist2bbox(xywh=True) (utils/tal.py:196-205).
+ *
+ *   lvl[t*L + l]  raw head tensor of task t, level l: [B, 64 + nc[t], H[l], W[l]]
+ *   y[t]          output [B, 4 + nc[t], A], A = sum_l H[l]*W[l]; rows cx, cy, w, h (pixels),
+ *                 then sigmoid class scores -- the layout Detect.forward returns.
+ *   strides[l]    pixel stride of level l (8, 16, 32 for P3..P5).
+ */
+int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
+                const float* strides, int dtype, void* const* y, void* stream);
+
+/* Bytes of device workspace cerb_nms / cerb_decode_nms need (0 unless max_det is large). */
+size_t cerb_nms_workspace_bytes(int T, int B, int max_det);
+
+/*
+ * Confidence filter, best-class / multi-label candidate expansion, top-k (max_nms)
+ * ordering, class-offset greedy NMS and the max_det cut for T task heads, every image
+ * of the batch, in one launch.
+ * Replaces non_max_suppression(prediction, conf_thres, iou_thres, classes, agnostic,
+ * multi_label, labels=(), max_det, nm=0)  (cerberusdet/utils/general.py:360-481),
+ * xywh2xyxy (:272-288) and the torchvision.ops.nms call at :464, as called per task by
+ * cerberusdet/cerberusdet_inference.py:125-135, val.py:318 and detect.py:99.
+ *
+ *   pred[t]     [B, 4 + nc[t], A] prediction of task t (what Detect.forward returns)
+ *   conf_thres, iou_thres   the Python floats; rounded inside exactly as torch does
+ *               (conf to the tensor dtype; IoU quotient compared in double)
+ *   classes     optional host list of class ids to keep (NULL / 0 = all)
+ *   max_nms     30000 in the reference (:416); max_wh 7680 (:415)
+ *   dets        out [T, B, max_det, 6] fp32 rows (x1, y1, x2, y2, conf, cls), score order;
+ *               only the first counts[t*B + b] rows of a segment are written
+ *   counts      out [T, B] int32
+ * Candidate order is "score descending, then (anchor, class) ascending" -- the stable
+ * form of the reference's sort at :459, whose tie order is unspecified.
+ */
+int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+             double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
+             int max_nms, double max_wh, float* dets, int* counts, void* workspace, size_t workspace_bytes,
+             void* stream);
+
+/*
+ * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy
+ * top-k so small inputs exercise the multi-chunk and radix-refinement paths.
+ * (0, 0) restores the defaults.  Results never depend on these values.
+ */
+int cerb_debug_set_chunking(int chunk_cap, int chunk_first);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CERB_POST_H */
