@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     };
 
     // ---------------- main loop over level-0 digit ranges, from the top
-    int hi0 = NMS_BINS;
+    int hi0 = NMS_BINS / 2;  // float sign bit is 0: digits < 2048, so (hi0 << 52) never overflows
     while (consumed < limit && kept < max_det && hi0 > 0) {
         const unsigned base = S.g0[hi0];
         if (S.g0[0] == base) break;  // nothing left below

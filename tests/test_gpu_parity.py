@@ -60,7 +60,7 @@ def test_decode_rejects_cpu_and_bad_shapes(ops):
     with pytest.raises(TypeError):
         ops.decode_heads(heads, STRIDES)
     bad = [[_dev(x) for x in heads[0]]]
-    bad[0][1] = bad[0][1][:, :, :3]
+    bad[0][1] = bad[0][1][:, :80].contiguous()  # wrong channel count for nc=20
     with pytest.raises(ValueError):
         ops.decode_heads(bad, STRIDES)
 
