@@ -19,7 +19,7 @@
 //    A bin that alone exceeds CAP (massive ties) is refined by deeper radix levels.
 //  * Suppression (:462-465): candidates are taken in tiles of 256; a tile is first
 //    tested against the kept list (shared memory), then resolved internally with a
-//    256x256 IoU bitmask and a ballot sweep by one warp.  IoU arithmetic reproduces
+//    256x256 IoU bitmask and a ballot fixpoint iteration (equal to the sequential sweep).  IoU arithmetic reproduces
 //    torchvision's CPU kernel: separately rounded fp32 ops on class-offset boxes, strict
 //    '>' against the threshold (the double-precision compare is folded into iou_thr).
 #include "cerb_kernels.h"
@@ -44,7 +44,7 @@ struct __align__(16) NmsSmem {
     int tcls[NMS_TILE];
     u64 mask[NMS_TILE][NMS_TILE_WORDS];
     u64 keepmask[NMS_TILE_WORDS];
-    unsigned alive32[NMS_TILE / 32];
+    unsigned keep32[2][NMS_TILE / 32];
     unsigned char tdead[NMS_TILE];
     unsigned warp_tot[NMS_THREADS / 32];
     unsigned counter;
@@ -69,31 +69,118 @@ __device__ __forceinline__ bool suppresses(const float4 bi, const float ai, cons
     return __fdiv_rn(inter, uni) > thr;
 }
 
-// ---- enumerate the candidate keys of one segment; f(key) is called once per candidate.
+// ---- enumerate the candidates of one segment; f(score_bits, anchor, class) is called once per
+// candidate.  Scores are read with 128-bit loads (the class planes of one image are one contiguous
+// [nc*A] array) whenever A is a multiple of the vector width and the base is 16-byte aligned.
+__device__ __forceinline__ unsigned make_sbits(float s) { return __float_as_uint(s); }
+__device__ __forceinline__ u64 make_key(unsigned sbits, unsigned idx) {
+    return ((u64)sbits << 32) | (u64)(0xFFFFFFFFu - idx);
+}
+
+template <typename T> struct ScoreVec {
+    static constexpr int V = 16 / sizeof(T);
+    union { uint4 raw; T e[16 / sizeof(T)]; };
+};
+
+#define SCAN_UNROLL 4
+
 template <typename T, bool MULTI, typename F>
 __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, int nc, int A, float thr,
                                                    const NmsParams& P, F f) {
+    constexpr int V = ScoreVec<T>::V;
     const T* __restrict__ sc = img + (size_t)4 * A;
+    const bool vec_ok = (A % V == 0) && ((reinterpret_cast<uintptr_t>(sc) & 15) == 0);
+    const bool filt = P.use_class_filter != 0;
     if (MULTI) {
-        for (int c = 0; c < nc; ++c) {
-            if (P.use_class_filter && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
-            const T* __restrict__ row = sc + (size_t)c * A;
-            for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
-                const float s = to_f32<T>(__ldg(row + a));
-                if (s > thr) f(((u64)__float_as_uint(s) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(a * nc + c)));
+        if (vec_ok) {
+            const unsigned nvec = (unsigned)(((u64)nc * (u64)A) / V);
+            for (unsigned i0 = threadIdx.x; i0 < nvec; i0 += NMS_THREADS * SCAN_UNROLL) {
+                ScoreVec<T> v[SCAN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u) {
+                    const unsigned i = i0 + u * NMS_THREADS;
+                    if (i < nvec) v[u].raw = __ldg(reinterpret_cast<const uint4*>(sc) + i);
+                }
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u) {
+                    const unsigned i = i0 + u * NMS_THREADS;
+                    if (i >= nvec) break;
+                    const unsigned e0 = i * V;
+                    const unsigned c = e0 / (unsigned)A;
+                    const unsigned a0 = e0 - c * (unsigned)A;
+                    if (filt && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float s = to_f32<T>(v[u].e[k]);
+                        if (s > thr) f(make_sbits(s), (int)(a0 + k), (int)c);
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < nc; ++c) {
+                if (filt && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
+                const T* __restrict__ row = sc + (size_t)c * A;
+                for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
+                    const float s = to_f32<T>(__ldg(row + a));
+                    if (s > thr) f(make_sbits(s), a, c);
+                }
             }
         }
     } else {
-        for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
-            float best = to_f32<T>(__ldg(sc + a));
-            int bc = 0;
-            for (int c = 1; c < nc; ++c) {
-                const float s = to_f32<T>(__ldg(sc + (size_t)c * A + a));
-                if (s > best) { best = s; bc = c; }  // lowest index wins ties (torch.max)
+        if (vec_ok) {
+            const int nv = A / V;
+            for (int i = threadIdx.x; i < nv; i += NMS_THREADS) {
+                const uint4* __restrict__ col = reinterpret_cast<const uint4*>(sc) + i;
+                float best[V];
+                int bc[V];
+                {
+                    ScoreVec<T> v0;
+                    v0.raw = __ldg(col);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) { best[k] = to_f32<T>(v0.e[k]); bc[k] = 0; }
+                }
+                int c = 1;
+                for (; c + SCAN_UNROLL <= nc; c += SCAN_UNROLL) {
+                    ScoreVec<T> v[SCAN_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < SCAN_UNROLL; ++u) v[u].raw = __ldg(col + (size_t)(c + u) * nv);
+#pragma unroll
+                    for (int u = 0; u < SCAN_UNROLL; ++u)
+#pragma unroll
+                        for (int k = 0; k < V; ++k) {
+                            const float s = to_f32<T>(v[u].e[k]);
+                            if (s > best[k]) { best[k] = s; bc[k] = c + u; }  // lowest index wins ties (torch.max)
+                        }
+                }
+                for (; c < nc; ++c) {
+                    ScoreVec<T> v1;
+                    v1.raw = __ldg(col + (size_t)c * nv);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float s = to_f32<T>(v1.e[k]);
+                        if (s > best[k]) { best[k] = s; bc[k] = c; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if (best[k] > thr) {
+                        if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
+                        f(make_sbits(best[k]), i * V + k, bc[k]);
+                    }
+                }
             }
-            if (best > thr) {
-                if (P.use_class_filter && !((P.class_mask[bc >> 5] >> (bc & 31)) & 1u)) continue;
-                f(((u64)__float_as_uint(best) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(a * nc + bc)));
+        } else {
+            for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
+                float best = to_f32<T>(__ldg(sc + a));
+                int bc = 0;
+                for (int c = 1; c < nc; ++c) {
+                    const float s = to_f32<T>(__ldg(sc + (size_t)c * A + a));
+                    if (s > best) { best = s; bc = c; }  // lowest index wins ties (torch.max)
+                }
+                if (best > thr) {
+                    if (filt && !((P.class_mask[bc >> 5] >> (bc & 31)) & 1u)) continue;
+                    f(make_sbits(best), a, bc);
+                }
             }
         }
     }
@@ -165,7 +252,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     // ---------------- level-0 histogram over every candidate of the segment
     for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
     __syncthreads();
-    for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) { atomicAdd(&S.g0[(unsigned)(key >> 52)], 1u); });
+    for_each_candidate<T, MULTI>(img, nc, A, thr, P,
+                                 [&](unsigned sb, int, int) { atomicAdd(&S.g0[sb >> 20], 1u); });
     __syncthreads();
     suffix_scan(S.g0, S.warp_tot);
 
@@ -245,46 +333,63 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 }
             }
             __syncthreads();
-            // C: pairwise mask inside the tile; item = (i, word)
+            // C: who suppresses whom inside the tile.  mask[j][w] = bits of the earlier candidates
+            //    i in word w (i < j, both alive) that would suppress j.  item = (j, word).
             if (tid < NMS_TILE) {
                 const unsigned al = __ballot_sync(0xffffffffu, S.tdead[tid] == 0);
-                if (lane == 0) S.alive32[wid] = al;
+                if (lane == 0) S.keep32[0][wid] = al;
             }
             for (int item = tid; item < NMS_TILE * NMS_TILE_WORDS; item += NMS_THREADS) {
-                const int i = item & (NMS_TILE - 1), w = item >> 8;
+                const int j = item & (NMS_TILE - 1), w = item >> 8;
                 u64 bits = 0;
-                if (i < nt && !S.tdead[i] && (w * 64 + 63) > i) {
-                    const float4 bi = S.tbox[i];
-                    const float ai = S.tarea[i];
-                    const int j0 = w * 64;
-                    const int jend = min(64, nt - j0);
-                    for (int jj = 0; jj < jend; ++jj) {
-                        const int j = j0 + jj;
-                        if (j > i && !S.tdead[j] && suppresses(bi, ai, S.tbox[j], S.tarea[j], iou_thr))
-                            bits |= 1ull << jj;
+                if (j < nt && !S.tdead[j] && w * 64 < j) {
+                    const float4 bj = S.tbox[j];
+                    const float aj = S.tarea[j];
+                    const int i0 = w * 64;
+                    const int iend = min(64, j - i0);
+                    for (int ii = 0; ii < iend; ++ii) {
+                        const int i = i0 + ii;
+                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], bj, aj, iou_thr)) bits |= 1ull << ii;
                     }
                 }
-                S.mask[i][w] = bits;
+                S.mask[j][w] = bits;
             }
             __syncthreads();
-            // D: greedy sweep over the tile by warp 0 (lane l < 4 owns word l)
-            if (wid == 0) {
-                u64 alive_w = 0, rem_w = 0, keep_w = 0;
-                if (lane < NMS_TILE_WORDS)
-                    alive_w = ((u64)S.alive32[2 * lane + 1] << 32) | (u64)S.alive32[2 * lane];
-                int budget = max_det - kept;
-                while (budget > 0) {
-                    const u64 cand = alive_w & ~rem_w;
-                    const unsigned vote = __ballot_sync(0xffffffffu, cand != 0ull);
-                    if (!vote) break;
-                    const int src = __ffs(vote) - 1;
-                    const int bit = __shfl_sync(0xffffffffu, __ffsll((long long)cand) - 1, src);
-                    const int i = src * 64 + bit;
-                    if (lane == src) { keep_w |= 1ull << bit; alive_w &= ~(1ull << bit); }
-                    if (lane < NMS_TILE_WORDS) rem_w |= S.mask[i][lane];
-                    --budget;
+            // D: greedy result as the fixpoint of  keep[j] = alive[j] && no kept earlier i suppresses j.
+            //    It is unique (keep[j] depends only on lower indices) and after r rounds the first r
+            //    candidates are final, so the loop ends in <= nt rounds -- in practice a handful.
+            {
+                u64 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                bool alive = false;
+                if (tid < NMS_TILE) {
+                    m0 = S.mask[tid][0]; m1 = S.mask[tid][1]; m2 = S.mask[tid][2]; m3 = S.mask[tid][3];
+                    alive = S.tdead[tid] == 0;
                 }
-                if (lane < NMS_TILE_WORDS) S.keepmask[lane] = keep_w;
+                int cur = 0;
+                for (;;) {
+                    int changed = 0;
+                    if (tid < NMS_TILE) {
+                        const unsigned* K = S.keep32[cur];
+                        const u64 k0 = ((u64)K[1] << 32) | K[0], k1 = ((u64)K[3] << 32) | K[2];
+                        const u64 k2 = ((u64)K[5] << 32) | K[4], k3 = ((u64)K[7] << 32) | K[6];
+                        const bool kj = alive && (((m0 & k0) | (m1 & k1) | (m2 & k2) | (m3 & k3)) == 0ull);
+                        const unsigned nw = __ballot_sync(0xffffffffu, kj);
+                        if (lane == 0) { S.keep32[cur ^ 1][wid] = nw; changed = (nw != K[wid]); }
+                    }
+                    cur ^= 1;
+                    if (!__syncthreads_or(changed)) break;
+                }
+                // first `budget` kept candidates only (greedy stops at max_det, general.py:465)
+                if (tid == 0) {
+                    int budget = max_det - kept;
+                    for (int w = 0; w < NMS_TILE_WORDS; ++w) {
+                        u64 kw = ((u64)S.keep32[cur][2 * w + 1] << 32) | S.keep32[cur][2 * w];
+                        int c = __popcll(kw);
+                        while (c > budget) { kw &= ~(1ull << (63 - __clzll((long long)kw))); --c; }
+                        budget -= c;
+                        S.keepmask[w] = kw;
+                    }
+                }
             }
             __syncthreads();
             // E: append the kept ones (in order) to the kept list and to the output
@@ -314,10 +419,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     auto collect = [&](u64 lo, u64 hi) -> unsigned {
         if (tid == 0) S.counter = 0;
         __syncthreads();
-        for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) {
-            if (key >= lo && key < hi) {
-                const unsigned p = atomicAdd(&S.counter, 1u);
-                if (p < NMS_CAP) S.keys[p] = key;
+        const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
+        for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int a, int c) {
+            if (sb >= sb_lo && sb <= sb_hi) {
+                const u64 key = make_key(sb, (unsigned)(a * nc + c));
+                if (key >= lo && key < hi) {
+                    const unsigned p = atomicAdd(&S.counter, 1u);
+                    if (p < NMS_CAP) S.keys[p] = key;
+                }
             }
         });
         __syncthreads();
@@ -337,8 +446,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             for (;;) {
                 for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g1[i] = 0;
                 __syncthreads();
-                for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](u64 key) {
-                    if (key >= lo && key < hi) atomicAdd(&S.g1[level_digit(key, lvl)], 1u);
+                const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
+                for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int a, int c) {
+                    if (sb >= sb_lo && sb <= sb_hi) {
+                        const u64 key = make_key(sb, (unsigned)(a * nc + c));
+                        if (key >= lo && key < hi) atomicAdd(&S.g1[level_digit(key, lvl)], 1u);
+                    }
                 });
                 __syncthreads();
                 suffix_scan(S.g1, S.warp_tot);
