@@ -21,6 +21,7 @@ EXPORTS = (
     "cerb_nms_workspace_bytes",
     "cerb_nms",
     "cerb_debug_set_chunking",
+    "cerb_debug_set_hist_sample",
 )
 
 _lib = None
@@ -55,6 +56,8 @@ def load() -> ctypes.CDLL:
     lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
+    lib.cerb_debug_set_hist_sample.restype = i
+    lib.cerb_debug_set_hist_sample.argtypes = [i]
     _lib = lib
     return lib
 

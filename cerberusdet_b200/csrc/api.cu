@@ -8,7 +8,7 @@
 #include "cerb_kernels.h"
 
 static thread_local char g_err[512] = "";
-static int g_chunk_cap = 0, g_chunk_first = 0;
+static int g_chunk_cap = 0, g_chunk_first = 0, g_hist_sample = 0;
 
 void cerb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -36,6 +36,12 @@ extern "C" int cerb_debug_set_chunking(int chunk_cap, int chunk_first) {
     REQUIRE(chunk_first >= 1, "chunk_first must be >= 1, got %d", chunk_first);
     g_chunk_cap = chunk_cap;
     g_chunk_first = chunk_first;
+    return 0;
+}
+
+extern "C" int cerb_debug_set_hist_sample(int stride) {
+    REQUIRE(stride >= 0 && stride <= 64, "hist sample stride must be in [0, 64], got %d", stride);
+    g_hist_sample = stride;
     return 0;
 }
 
@@ -158,10 +164,25 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
         P.kept_ws = (float*)workspace;
     }
     P.chunk_cap = g_chunk_cap ? g_chunk_cap : 4096;
-    int first = g_chunk_first ? g_chunk_first : (max_det + max_det / 2 + 64);
-    if (first < 256 && !g_chunk_first) first = 256;
+    int first = g_chunk_first ? g_chunk_first : (max_det + max_det / 8 + 32);
+    if (first < 128 && !g_chunk_first) first = 128;
     if (first > P.chunk_cap) first = P.chunk_cap;
     P.chunk_first = first;
+    P.hist_sample = g_hist_sample ? g_hist_sample : 8;
+    // class shortcut is exact iff fl(gap + fl(c*gap)) <= fl((c+1)*gap) for every class (true for 7680)
+    P.class_shortcut = 0;
+    if (!agnostic && P.class_gap > 0.f) {
+        int ncmax = 0;
+        for (int t = 0; t < T; ++t) ncmax = nc[t] > ncmax ? nc[t] : ncmax;
+        bool ok = true;
+        for (int c = 0; c + 1 < ncmax && ok; ++c) {
+            volatile float lo = (float)c * P.class_gap;
+            volatile float top = P.class_gap + lo;
+            volatile float nxt = (float)(c + 1) * P.class_gap;
+            ok = top <= nxt;
+        }
+        P.class_shortcut = ok ? 1 : 0;
+    }
     cudaError_t e = cerb_launch_nms(P, dtype, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         cerb_set_error("cerb_nms: launch failed: %s", cudaGetErrorString(e));

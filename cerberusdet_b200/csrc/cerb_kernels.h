@@ -37,6 +37,8 @@ struct NmsParams {
     float* kept_ws;  // global kept-list storage [T*B, max_det, 5] when max_det is too large for smem, else null
     int chunk_cap;   // candidates sorted per chunk (<= NMS_CAP); tests shrink it to force the rare paths
     int chunk_first; // size target of the first chunk
+    int hist_sample; // stride (in 16-byte vectors) of the estimating histogram; 1 = exact
+    int class_shortcut; // 1 if different-class tame boxes provably never intersect after the offset
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);

@@ -42,6 +42,7 @@ struct __align__(16) NmsSmem {
     float tarea[NMS_TILE];
     float tscore[NMS_TILE];
     int tcls[NMS_TILE];
+    int tcode[NMS_TILE];         // class id if the box is "tame" (see class shortcut), else -1
     u64 mask[NMS_TILE][NMS_TILE_WORDS];
     u64 keepmask[NMS_TILE_WORDS];
     unsigned keep32[2][NMS_TILE / 32];
@@ -50,6 +51,7 @@ struct __align__(16) NmsSmem {
     unsigned counter;
     float4 kbox[NMS_KEPT_SMEM];
     float karea[NMS_KEPT_SMEM];
+    int kcode[NMS_KEPT_SMEM];
 };
 
 // ---- IoU test exactly as torchvision's CPU kernel does it (std::max/std::min semantics,
@@ -86,7 +88,9 @@ template <typename T> struct ScoreVec {
 
 template <typename T, bool MULTI, typename F>
 __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, int nc, int A, float thr,
-                                                   const NmsParams& P, F f) {
+                                                   const NmsParams& P, F f, const unsigned vstride = 1) {
+    // vstride > 1 visits only every vstride-th 16-byte vector (multi-label vector path only): used for the
+    // *estimating* histogram; every exact pass uses vstride == 1.
     constexpr int V = ScoreVec<T>::V;
     const T* __restrict__ sc = img + (size_t)4 * A;
     const bool vec_ok = (A % V == 0) && ((reinterpret_cast<uintptr_t>(sc) & 15) == 0);
@@ -94,17 +98,19 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
     if (MULTI) {
         if (vec_ok) {
             const unsigned nvec = (unsigned)(((u64)nc * (u64)A) / V);
-            for (unsigned i0 = threadIdx.x; i0 < nvec; i0 += NMS_THREADS * SCAN_UNROLL) {
+            const unsigned nvis = (nvec + vstride - 1) / vstride;  // vectors visited
+            for (unsigned q0 = threadIdx.x; q0 < nvis; q0 += NMS_THREADS * SCAN_UNROLL) {
                 ScoreVec<T> v[SCAN_UNROLL];
 #pragma unroll
                 for (int u = 0; u < SCAN_UNROLL; ++u) {
-                    const unsigned i = i0 + u * NMS_THREADS;
-                    if (i < nvec) v[u].raw = __ldg(reinterpret_cast<const uint4*>(sc) + i);
+                    const unsigned q = q0 + u * NMS_THREADS;
+                    if (q < nvis) v[u].raw = __ldg(reinterpret_cast<const uint4*>(sc) + (size_t)q * vstride);
                 }
 #pragma unroll
                 for (int u = 0; u < SCAN_UNROLL; ++u) {
-                    const unsigned i = i0 + u * NMS_THREADS;
-                    if (i >= nvec) break;
+                    const unsigned q = q0 + u * NMS_THREADS;
+                    if (q >= nvis) break;
+                    const unsigned i = q * vstride;
                     const unsigned e0 = i * V;
                     const unsigned c = e0 / (unsigned)A;
                     const unsigned a0 = e0 - c * (unsigned)A;
@@ -243,22 +249,40 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
     float4* kbox = S.kbox;
     float* karea = S.karea;
+    int* kcode = S.kcode;
     if (max_det > NMS_KEPT_SMEM) {
-        float* ws = P.kept_ws + (size_t)seg * max_det * 5;
+        float* ws = P.kept_ws + (size_t)seg * max_det * 6;
         kbox = reinterpret_cast<float4*>(ws);
         karea = ws + (size_t)max_det * 4;
+        kcode = reinterpret_cast<int*>(ws + (size_t)max_det * 5);
     }
+    // Class shortcut: with class-offset boxes (general.py:462-463) two boxes of different classes
+    // whose un-offset corners all lie in [0, max_wh) can never intersect, so their IoU test is
+    // skipped.  The host verified that the fp32 offsets make this exact (P.class_shortcut).
+    const bool shortcut = P.class_shortcut != 0;
 
-    // ---------------- level-0 histogram over every candidate of the segment
-    for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
-    __syncthreads();
-    for_each_candidate<T, MULTI>(img, nc, A, thr, P,
-                                 [&](unsigned sb, int, int) { atomicAdd(&S.g0[sb >> 20], 1u); });
-    __syncthreads();
-    suffix_scan(S.g0, S.warp_tot);
+    // ---------------- level-0 histogram (top 12 key bits).  For large multi-label segments it is an
+    // ESTIMATE built from every hstride-th score vector: chunk boundaries only steer how much is
+    // gathered at once; what a chunk contains, its order and every count that matters (collect)
+    // are exact.  A chunk that turns out too large switches the segment to the exact histogram.
+    const unsigned max_nms = (unsigned)max(P.max_nms, 0);
+    unsigned hstride = 1;
+    if (MULTI && P.hist_sample > 1) {
+        const u64 nvec = ((u64)nc * (u64)A) / ScoreVec<T>::V;
+        if (nvec >= 8192 && (A % ScoreVec<T>::V) == 0) hstride = (unsigned)P.hist_sample;
+    }
+    auto build_hist = [&](unsigned stride, unsigned below_digit) {
+        for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
+        __syncthreads();
+        for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int, int) {
+            const unsigned d = sb >> 20;
+            if (d < below_digit) atomicAdd(&S.g0[d], 1u);
+        }, stride);
+        __syncthreads();
+        suffix_scan(S.g0, S.warp_tot);
+    };
+    build_hist(hstride, NMS_BINS);
 
-    const unsigned total = S.g0[0];
-    const unsigned limit = min(total, (unsigned)max(P.max_nms, 0));
     unsigned consumed = 0;
     int kept = 0;
     unsigned target = min((unsigned)max(P.chunk_first, 1), cap);
@@ -314,6 +338,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                     S.tarea[tid] = __fmul_rn(__fsub_rn(o.z, o.x), __fsub_rn(o.w, o.y));
                     S.tscore[tid] = __uint_as_float((unsigned)(key >> 32));
                     S.tcls[tid] = c;
+                    const float g = P.class_gap;
+                    const bool tame = shortcut && r.x >= 0.f && r.y >= 0.f && r.z >= 0.f && r.w >= 0.f &&
+                                      r.x < g && r.y < g && r.z < g && r.w < g;
+                    S.tcode[tid] = tame ? c : -1;
                     dead = 0;
                 }
                 S.tdead[tid] = dead;
@@ -327,7 +355,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                     const int k0 = half ? mid : 0, k1 = half ? kept : mid;
                     const float4 bj = S.tbox[j];
                     const float aj = S.tarea[j];
+                    const int cj = S.tcode[j];
                     for (int k = k0; k < k1; ++k) {
+                        const int ck = kcode[k];
+                        if (ck != cj && (ck | cj) >= 0) continue;  // different classes, both tame
                         if (suppresses(kbox[k], karea[k], bj, aj, iou_thr)) { S.tdead[j] = 1; break; }
                     }
                 }
@@ -345,10 +376,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 if (j < nt && !S.tdead[j] && w * 64 < j) {
                     const float4 bj = S.tbox[j];
                     const float aj = S.tarea[j];
+                    const int cj = S.tcode[j];
                     const int i0 = w * 64;
                     const int iend = min(64, j - i0);
                     for (int ii = 0; ii < iend; ++ii) {
                         const int i = i0 + ii;
+                        const int ci = S.tcode[i];
+                        if (ci != cj && (ci | cj) >= 0) continue;  // different classes, both tame
                         if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], bj, aj, iou_thr)) bits |= 1ull << ii;
                     }
                 }
@@ -403,6 +437,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                     for (int ww = 0; ww < w; ++ww) pos += __popcll(S.keepmask[ww]);
                     kbox[pos] = S.tbox[tid];
                     karea[pos] = S.tarea[tid];
+                    kcode[pos] = S.tcode[tid];
                     const float4 r = S.traw[tid];
                     float* o = dets + (size_t)pos * 6;  // general.py:474 rows (x1,y1,x2,y2,conf,cls)
                     o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
@@ -439,7 +474,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     auto overflow_bin = [&](int bin) {
         const u64 lowlim = (u64)bin << 52;
         u64 bnd = (u64)(bin + 1) << 52;
-        while (consumed < limit && kept < max_det) {
+        while (consumed < max_nms && kept < max_det) {
             u64 lo = lowlim, hi = bnd, L = lowlim;
             int lvl = 1;
             bool empty = false;
@@ -458,7 +493,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 const unsigned tot = S.g1[0];
                 if (tot == 0) { empty = true; break; }
                 if (tot <= cap) { L = lo; break; }
-                const unsigned need = min(cap, limit - consumed);
+                const unsigned need = min(cap, max_nms - consumed);
                 const int nb = lvl < 5 ? NMS_BINS : 16;
                 const int sh = level_shift(lvl);
                 const u64 parent = lvl < 5 ? (lo >> (sh + 12)) << (sh + 12) : (lo >> 4) << 4;
@@ -478,7 +513,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             if (empty) return;
             if (L < lowlim) L = lowlim;
             const unsigned n = collect(L, bnd);
-            const unsigned take = min(n, limit - consumed);
+            const unsigned take = min(n, max_nms - consumed);
             consume_chunk(n, take);
             consumed += take;
             bnd = L;
@@ -488,27 +523,37 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
     // ---------------- main loop over level-0 digit ranges, from the top
     int hi0 = NMS_BINS / 2;  // float sign bit is 0: digits < 2048, so (hi0 << 52) never overflows
-    while (consumed < limit && kept < max_det && hi0 > 0) {
+    while (hi0 > 0 && consumed < max_nms && kept < max_det) {
         const unsigned base = S.g0[hi0];
-        if (S.g0[0] == base) break;  // nothing left below
-        const unsigned remaining = S.g0[0] - base;
-        const unsigned need = min(min(target, limit - consumed), remaining);
-        const int d = find_digit(S.g0, hi0, base, need);
-        const unsigned cnt = S.g0[d] - base;
-        int lo0 = d;
-        if (cnt > cap) {
-            const unsigned c1 = S.g0[d + 1] - base;
-            if (c1 > 0) {
-                lo0 = d + 1;
-            } else {
-                overflow_bin(d);
-                hi0 = d;
-                target = cap;
-                continue;
+        const unsigned rem_s = S.g0[0] - base;  // candidates left below hi0, in histogram units
+        if (hstride == 1 && rem_s == 0) break;
+        const unsigned need = min(target, max_nms - consumed);
+        const unsigned need_s = hstride == 1 ? need : (need + need / 4 + hstride - 1) / hstride;  // +25% margin
+        int lo0 = 0;
+        bool single_heavy = false;
+        if (rem_s > need_s) {
+            const int d = find_digit(S.g0, hi0, base, need_s);
+            lo0 = d;
+            const unsigned est = (S.g0[d] - base) * hstride;
+            if (est > (hstride == 1 ? cap : cap - cap / 4)) {
+                if (S.g0[d + 1] - base > 0) lo0 = d + 1;
+                else single_heavy = (hstride == 1);  // exact: digit d alone exceeds the capacity
             }
         }
+        if (single_heavy) {
+            overflow_bin(lo0);
+            hi0 = lo0;
+            target = cap;
+            continue;
+        }
         const unsigned n = collect((u64)lo0 << 52, (u64)hi0 << 52);
-        const unsigned take = min(n, limit - consumed);
+        if (n > cap) {
+            // estimate was off (or ties piled up): count exactly what is left and retry
+            build_hist(1u, (unsigned)hi0);
+            hstride = 1;
+            continue;
+        }
+        const unsigned take = min(n, max_nms - consumed);
         consume_chunk(n, take);
         consumed += take;
         hi0 = lo0;
@@ -520,7 +565,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
     if (max_det <= NMS_KEPT_SMEM) return 0;
-    return (size_t)T * B * max_det * 5 * sizeof(float);
+    return (size_t)T * B * max_det * 6 * sizeof(float);
 }
 
 template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParams& P, cudaStream_t stream) {

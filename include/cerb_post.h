@@ -93,6 +93,13 @@ int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dt
  */
 int cerb_debug_set_chunking(int chunk_cap, int chunk_first);
 
+/*
+ * Test hook: stride (in 16-byte score vectors) of the estimating histogram that sizes the
+ * chunks of large multi-label segments; 1 = always exact, 0 = default (8).  Results never
+ * depend on it.
+ */
+int cerb_debug_set_hist_sample(int stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,46 @@ def test_nms_constant_scores_massive_ties(ops, dtype):
         _assert_rows_equal(got, want, str(kw))
 
 
+def _truncation_prediction(dtype, seed=3):
+    """> 30000 multi-label candidates, nearly all inside one heavy cluster (suppressed by its top box)
+    plus isolated boxes whose scores straddle the rank-30000 cut: the kept set is sensitive to the exact
+    max_nms truncation (utils/general.py:459) and the whole candidate list has to be consumed."""
+    g = torch.Generator().manual_seed(seed)
+    A, nc = 12000, 4
+    y = torch.empty(1, 4 + nc, A)
+    y[0, 0] = 320 + torch.randn(A, generator=g)
+    y[0, 1] = 320 + torch.randn(A, generator=g)
+    y[0, 2] = 200 + torch.randn(A, generator=g)
+    y[0, 3] = 200 + torch.randn(A, generator=g)
+    y[0, 4:] = torch.rand(nc, A, generator=g) * 0.9 + 0.01
+    iso = torch.randperm(A, generator=g)[:60]
+    gx = (torch.arange(60) % 10) * 60.0 + 15
+    gy = (torch.arange(60) // 10) * 60.0 + 615  # far below the cluster
+    y[0, 0, iso], y[0, 1, iso] = gx, gy
+    y[0, 2, iso] = 8.0
+    y[0, 3, iso] = 8.0
+    return y.to(dtype)
+
+
+@pytest.mark.parametrize("sample", [0, 1, 3, 16])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_nms_max_nms_truncation_full_consumption(ops, dtype, sample):
+    from cerberusdet_b200 import _lib
+    from cerberusdet_b200.nms import non_max_suppression
+    from oracle import ref_port as rp
+
+    pred = _truncation_prediction(dtype)
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
+    want = rp.nms_port(pred, greedy="c", **kw)
+    assert 20 < want[0].shape[0] < 300  # neither trivially empty nor capped by max_det
+    assert _lib.load().cerb_debug_set_hist_sample(sample) == 0
+    try:
+        got = non_max_suppression(_dev(pred), **kw)
+    finally:
+        _lib.load().cerb_debug_set_hist_sample(0)
+    _assert_rows_equal(got, want, f"sample={sample}")
+
+
 def test_nms_empty_and_edge_batches(ops):
     from cerberusdet_b200.nms import non_max_suppression
 
@@ -191,6 +231,16 @@ def test_full_size_properties_cfg3(ops):
             assert (s[:-1] >= s[1:]).all()  # score-descending
             assert (s > 0.001).all()
             assert ((d[:, 5] >= 0) & (d[:, 5] < ncs[t])).all()
+    # the estimating histogram never changes results: exact histogram gives the same bits
+    from cerberusdet_b200 import _lib
+
+    for stride in (1, 16):
+        _lib.load().cerb_debug_set_hist_sample(stride)
+        try:
+            d1, c1 = ops.nms_batched(ys, **kw)
+        finally:
+            _lib.load().cerb_debug_set_hist_sample(0)
+        assert torch.equal(c1, counts) and torch.equal(d1, dets)
     # shard invariance: running images 16..31 alone gives the same rows
     ys_shard = [y[16:32].contiguous() for y in ys]
     d2, c2 = ops.nms_batched(ys_shard, **kw)
