@@ -169,19 +169,19 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
     if (first > P.chunk_cap) first = P.chunk_cap;
     P.chunk_first = first;
     P.hist_sample = g_hist_sample ? g_hist_sample : 8;
-    // class shortcut is exact iff fl(gap + fl(c*gap)) <= fl((c+1)*gap) for every class (true for 7680)
+    // Class shortcut (see nms.cu): exact when the offsets and the window ends are integers small enough
+    // for every fp32 sum  coordinate-bound + class * gap  to be exact (true for the reference's 7680).
     P.class_shortcut = 0;
-    if (!agnostic && P.class_gap > 0.f) {
+    if (!agnostic && P.class_gap >= 8.f) {
         int ncmax = 0;
         for (int t = 0; t < T; ++t) ncmax = nc[t] > ncmax ? nc[t] : ncmax;
-        bool ok = true;
-        for (int c = 0; c + 1 < ncmax && ok; ++c) {
-            volatile float lo = (float)c * P.class_gap;
-            volatile float top = P.class_gap + lo;
-            volatile float nxt = (float)(c + 1) * P.class_gap;
-            ok = top <= nxt;
+        const double gap = (double)P.class_gap;
+        const double lo = -floor(gap / 8.0);
+        if (gap == floor(gap) && gap * (double)(ncmax + 1) < 8388608.0) {
+            P.class_shortcut = 1;
+            P.tame_lo = (float)lo;
+            P.tame_hi = (float)(lo + gap);
         }
-        P.class_shortcut = ok ? 1 : 0;
     }
     cudaError_t e = cerb_launch_nms(P, dtype, (cudaStream_t)stream);
     if (e != cudaSuccess) {

@@ -39,6 +39,7 @@ struct NmsParams {
     int chunk_first; // size target of the first chunk
     int hist_sample; // stride (in 16-byte vectors) of the estimating histogram; 1 = exact
     int class_shortcut; // 1 if different-class tame boxes provably never intersect after the offset
+    float tame_lo, tame_hi; // the window of "tame" un-offset coordinates, tame_hi - tame_lo == class_gap
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);

@@ -17,41 +17,42 @@
 //    chunk is gathered, bitonic-sorted in shared memory and consumed; the kernel stops
 //    as soon as max_det boxes are kept or max_nms candidates (:459) were consumed.
 //    A bin that alone exceeds CAP (massive ties) is refined by deeper radix levels.
-//  * Suppression (:462-465): candidates are taken in tiles of 256; a tile is first
-//    tested against the kept list (shared memory), then resolved internally with a
-//    256x256 IoU bitmask and a ballot fixpoint iteration (equal to the sequential sweep).  IoU arithmetic reproduces
+//  * Suppression (:462-465): candidates are taken in tiles of 512, one per thread; a
+//    candidate is first tested against the kept list (shared memory), then the tile is
+//    resolved internally with a per-thread suppressor bitmask and a ballot fixpoint
+//    iteration (equal to the sequential sweep).  Per-class chains skip the pairs that the
+//    class offset makes disjoint.  IoU arithmetic reproduces
 //    torchvision's CPU kernel: separately rounded fp32 ops on class-offset boxes, strict
 //    '>' against the threshold (the double-precision compare is folded into iou_thr).
 #include "cerb_kernels.h"
 
 #define NMS_THREADS 512
-#define NMS_TILE 256
+#define NMS_TILE 512         // == NMS_THREADS: one candidate per thread
 #define NMS_TILE_WORDS (NMS_TILE / 64)
 #define NMS_CAP 4096         // max keys sorted at once
 #define NMS_BINS 4096        // 12-bit radix digits
 #define NMS_KEPT_SMEM 1024   // kept list lives in smem up to this max_det
+#define NMS_BUCKETS 1024     // class buckets of the kept-list chains (class & 1023)
 
 typedef unsigned long long u64;
 
 struct __align__(16) NmsSmem {
-    unsigned g0[NMS_BINS + 8];   // level-0: G0[d] = #keys with digit >= d ; G0[4096] = 0
+    unsigned g0[NMS_BINS + 8];   // level-0: G0[d] = #keys with digit >= d (histogram units); G0[4096] = 0
     unsigned g1[NMS_BINS + 8];   // scratch for deeper levels
     u64 keys[NMS_CAP];
     float4 tbox[NMS_TILE];       // class-offset corners of the tile's candidates
-    float4 traw[NMS_TILE];       // un-offset corners (output)
     float tarea[NMS_TILE];
-    float tscore[NMS_TILE];
-    int tcls[NMS_TILE];
-    int tcode[NMS_TILE];         // class id if the box is "tame" (see class shortcut), else -1
-    u64 mask[NMS_TILE][NMS_TILE_WORDS];
-    u64 keepmask[NMS_TILE_WORDS];
+    int tcode[NMS_TILE];         // class id if the box is "tame" (see class shortcut), -1 wild, -2 padding
+    int tprev[NMS_TILE];         // previous candidate of the same class inside the tile, or -1
     unsigned keep32[2][NMS_TILE / 32];
     unsigned char tdead[NMS_TILE];
     unsigned warp_tot[NMS_THREADS / 32];
     unsigned counter;
+    int tile_wild, kept_wild;
+    int khead[NMS_BUCKETS];      // newest kept box of each class bucket, or -1
+    int knext_s[NMS_KEPT_SMEM];  // next kept box of the same bucket
     float4 kbox[NMS_KEPT_SMEM];
     float karea[NMS_KEPT_SMEM];
-    int kcode[NMS_KEPT_SMEM];
 };
 
 // ---- IoU test exactly as torchvision's CPU kernel does it (std::max/std::min semantics,
@@ -249,17 +250,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
     float4* kbox = S.kbox;
     float* karea = S.karea;
-    int* kcode = S.kcode;
     if (max_det > NMS_KEPT_SMEM) {
-        float* ws = P.kept_ws + (size_t)seg * max_det * 6;
+        float* ws = P.kept_ws + (size_t)seg * max_det * 5;
         kbox = reinterpret_cast<float4*>(ws);
         karea = ws + (size_t)max_det * 4;
-        kcode = reinterpret_cast<int*>(ws + (size_t)max_det * 5);
     }
-    // Class shortcut: with class-offset boxes (general.py:462-463) two boxes of different classes
-    // whose un-offset corners all lie in [0, max_wh) can never intersect, so their IoU test is
-    // skipped.  The host verified that the fp32 offsets make this exact (P.class_shortcut).
-    const bool shortcut = P.class_shortcut != 0;
+    // Class shortcut.  Boxes are offset by class * max_wh before NMS (general.py:462-463), so two boxes
+    // of different classes whose un-offset corners all lie in the window [tame_lo, tame_hi) of width
+    // max_wh can never intersect (the host checked that the fp32 offsets are exact, P.class_shortcut).
+    // While every box involved is such a "tame" box, a candidate is only tested against the kept /
+    // earlier boxes of its own class, found through per-class chains; one wild box anywhere (or
+    // agnostic mode, or a kept list too large for shared memory) switches to testing all pairs.
+    const bool shortcut = P.class_shortcut != 0 && max_det <= NMS_KEPT_SMEM;
+    bool kept_wild = false;
+    for (int i = tid; i < NMS_BUCKETS; i += NMS_THREADS) S.khead[i] = -1;
+    if (tid == 0) S.kept_wild = 0;
 
     // ---------------- level-0 histogram (top 12 key bits).  For large multi-label segments it is an
     // ESTIMATE built from every hstride-th score vector: chunk boundaries only steer how much is
@@ -307,146 +312,147 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 __syncthreads();
             }
         }
-        // tiles
+        // tiles: one candidate per thread
         for (unsigned t0 = 0; t0 < take && kept < max_det; t0 += NMS_TILE) {
             const int nt = (int)min((unsigned)NMS_TILE, take - t0);
             // A: materialise the tile's boxes  (general.py:443 xywh2xyxy in dtype, :462-463 class offset in fp32)
-            if (tid < NMS_TILE) {
-                unsigned char dead = 1;
-                if (tid < nt) {
-                    const u64 key = S.keys[t0 + tid];
-                    const unsigned idx = 0xFFFFFFFFu - (unsigned)key;
-                    const int a = idx / nc, c = idx - a * nc;
-                    const float cx = to_f32<T>(__ldg(img + a));
-                    const float cy = to_f32<T>(__ldg(img + (size_t)A + a));
-                    const float bw = to_f32<T>(__ldg(img + (size_t)2 * A + a));
-                    const float bh = to_f32<T>(__ldg(img + (size_t)3 * A + a));
-                    const float hw_ = rnd<T>(bw * 0.5f), hh_ = rnd<T>(bh * 0.5f);
-                    float4 r;
-                    r.x = rnd<T>(__fsub_rn(cx, hw_));
-                    r.y = rnd<T>(__fsub_rn(cy, hh_));
-                    r.z = rnd<T>(__fadd_rn(cx, hw_));
-                    r.w = rnd<T>(__fadd_rn(cy, hh_));
-                    const float off = __fmul_rn((float)c, P.class_gap);
-                    float4 o;
-                    o.x = __fadd_rn(r.x, off);
-                    o.y = __fadd_rn(r.y, off);
-                    o.z = __fadd_rn(r.z, off);
-                    o.w = __fadd_rn(r.w, off);
-                    S.traw[tid] = r;
-                    S.tbox[tid] = o;
-                    S.tarea[tid] = __fmul_rn(__fsub_rn(o.z, o.x), __fsub_rn(o.w, o.y));
-                    S.tscore[tid] = __uint_as_float((unsigned)(key >> 32));
-                    S.tcls[tid] = c;
-                    const float g = P.class_gap;
-                    const bool tame = shortcut && r.x >= 0.f && r.y >= 0.f && r.z >= 0.f && r.w >= 0.f &&
-                                      r.x < g && r.y < g && r.z < g && r.w < g;
-                    S.tcode[tid] = tame ? c : -1;
-                    dead = 0;
-                }
-                S.tdead[tid] = dead;
-            }
+            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), box = raw;
+            float area = 0.f, score = 0.f;
+            int cls = 0, code = -1;
+            bool dead = true;
+            if (tid == 0) S.tile_wild = 0;
             __syncthreads();
-            // B: against the kept list (two threads per candidate, each takes half of the list)
+            if (tid < nt) {
+                const u64 key = S.keys[t0 + tid];
+                const unsigned idx = 0xFFFFFFFFu - (unsigned)key;
+                const int a = idx / nc;
+                cls = idx - a * nc;
+                const float cx = to_f32<T>(__ldg(img + a));
+                const float cy = to_f32<T>(__ldg(img + (size_t)A + a));
+                const float bw = to_f32<T>(__ldg(img + (size_t)2 * A + a));
+                const float bh = to_f32<T>(__ldg(img + (size_t)3 * A + a));
+                const float hw_ = rnd<T>(bw * 0.5f), hh_ = rnd<T>(bh * 0.5f);
+                raw.x = rnd<T>(__fsub_rn(cx, hw_));
+                raw.y = rnd<T>(__fsub_rn(cy, hh_));
+                raw.z = rnd<T>(__fadd_rn(cx, hw_));
+                raw.w = rnd<T>(__fadd_rn(cy, hh_));
+                const float off = __fmul_rn((float)cls, P.class_gap);
+                box.x = __fadd_rn(raw.x, off);
+                box.y = __fadd_rn(raw.y, off);
+                box.z = __fadd_rn(raw.z, off);
+                box.w = __fadd_rn(raw.w, off);
+                area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
+                score = __uint_as_float((unsigned)(key >> 32));
+                const float lo = P.tame_lo, hi = P.tame_hi;
+                const bool tame = raw.x >= lo && raw.y >= lo && raw.z >= lo && raw.w >= lo &&
+                                  raw.x < hi && raw.y < hi && raw.z < hi && raw.w < hi;
+                code = tame ? cls : -1;
+                if (!tame) S.tile_wild = 1;
+                dead = false;
+            }
+            S.tbox[tid] = box;
+            S.tarea[tid] = area;
+            S.tcode[tid] = dead ? -2 : code;  // -2: padding, never equal to a class
+            __syncthreads();
+            // Per-class chains are valid while every box involved is tame (see the class shortcut above).
+            const bool fast = shortcut && !S.tile_wild && !kept_wild;
+            int prev = -1;
+            if (fast && !dead) {  // previous candidate of the same class inside the tile
+                int p = tid - 1;
+                while (p >= 0 && S.tcode[p] != code) --p;
+                prev = p;
+            }
+            S.tprev[tid] = prev;
+            // B: against the kept list
+            if (!dead && kept > 0) {
+                if (fast) {
+                    for (int k = S.khead[cls & (NMS_BUCKETS - 1)]; k >= 0; k = S.knext_s[k]) {
+                        if (suppresses(kbox[k], karea[k], box, area, iou_thr)) { dead = true; break; }
+                    }
+                } else {
+                    for (int k = 0; k < kept; ++k) {
+                        if (suppresses(kbox[k], karea[k], box, area, iou_thr)) { dead = true; break; }
+                    }
+                }
+            }
+            S.tdead[tid] = dead ? 1 : 0;
+            __syncthreads();
+            // C: m[w] = bits of the earlier candidates i in word w (alive) that would suppress this one
+            u64 m[NMS_TILE_WORDS];
+#pragma unroll
+            for (int w = 0; w < NMS_TILE_WORDS; ++w) m[w] = 0ull;
+            if (!dead) {
+                if (fast) {
+                    for (int i = prev; i >= 0; i = S.tprev[i]) {
+                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) {
+                            const u64 bit = 1ull << (i & 63);
+#pragma unroll
+                            for (int w = 0; w < NMS_TILE_WORDS; ++w)
+                                if (w == (i >> 6)) m[w] |= bit;
+                        }
+                    }
+                } else {
+                    for (int i = 0; i < tid; ++i) {
+                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) {
+                            const u64 bit = 1ull << (i & 63);
+#pragma unroll
+                            for (int w = 0; w < NMS_TILE_WORDS; ++w)
+                                if (w == (i >> 6)) m[w] |= bit;
+                        }
+                    }
+                }
+            }
             {
-                const int j = tid & (NMS_TILE - 1), half = tid >> 8;
-                if (j < nt && kept > 0) {
-                    const int mid = (kept + 1) >> 1;
-                    const int k0 = half ? mid : 0, k1 = half ? kept : mid;
-                    const float4 bj = S.tbox[j];
-                    const float aj = S.tarea[j];
-                    const int cj = S.tcode[j];
-                    for (int k = k0; k < k1; ++k) {
-                        const int ck = kcode[k];
-                        if (ck != cj && (ck | cj) >= 0) continue;  // different classes, both tame
-                        if (suppresses(kbox[k], karea[k], bj, aj, iou_thr)) { S.tdead[j] = 1; break; }
-                    }
-                }
-            }
-            __syncthreads();
-            // C: who suppresses whom inside the tile.  mask[j][w] = bits of the earlier candidates
-            //    i in word w (i < j, both alive) that would suppress j.  item = (j, word).
-            if (tid < NMS_TILE) {
-                const unsigned al = __ballot_sync(0xffffffffu, S.tdead[tid] == 0);
+                const unsigned al = __ballot_sync(0xffffffffu, !dead);
                 if (lane == 0) S.keep32[0][wid] = al;
-            }
-            for (int item = tid; item < NMS_TILE * NMS_TILE_WORDS; item += NMS_THREADS) {
-                const int j = item & (NMS_TILE - 1), w = item >> 8;
-                u64 bits = 0;
-                if (j < nt && !S.tdead[j] && w * 64 < j) {
-                    const float4 bj = S.tbox[j];
-                    const float aj = S.tarea[j];
-                    const int cj = S.tcode[j];
-                    const int i0 = w * 64;
-                    const int iend = min(64, j - i0);
-                    for (int ii = 0; ii < iend; ++ii) {
-                        const int i = i0 + ii;
-                        const int ci = S.tcode[i];
-                        if (ci != cj && (ci | cj) >= 0) continue;  // different classes, both tame
-                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], bj, aj, iou_thr)) bits |= 1ull << ii;
-                    }
-                }
-                S.mask[j][w] = bits;
             }
             __syncthreads();
             // D: greedy result as the fixpoint of  keep[j] = alive[j] && no kept earlier i suppresses j.
             //    It is unique (keep[j] depends only on lower indices) and after r rounds the first r
             //    candidates are final, so the loop ends in <= nt rounds -- in practice a handful.
-            {
-                u64 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                bool alive = false;
-                if (tid < NMS_TILE) {
-                    m0 = S.mask[tid][0]; m1 = S.mask[tid][1]; m2 = S.mask[tid][2]; m3 = S.mask[tid][3];
-                    alive = S.tdead[tid] == 0;
-                }
-                int cur = 0;
-                for (;;) {
-                    int changed = 0;
-                    if (tid < NMS_TILE) {
-                        const unsigned* K = S.keep32[cur];
-                        const u64 k0 = ((u64)K[1] << 32) | K[0], k1 = ((u64)K[3] << 32) | K[2];
-                        const u64 k2 = ((u64)K[5] << 32) | K[4], k3 = ((u64)K[7] << 32) | K[6];
-                        const bool kj = alive && (((m0 & k0) | (m1 & k1) | (m2 & k2) | (m3 & k3)) == 0ull);
-                        const unsigned nw = __ballot_sync(0xffffffffu, kj);
-                        if (lane == 0) { S.keep32[cur ^ 1][wid] = nw; changed = (nw != K[wid]); }
-                    }
-                    cur ^= 1;
-                    if (!__syncthreads_or(changed)) break;
-                }
-                // first `budget` kept candidates only (greedy stops at max_det, general.py:465)
-                if (tid == 0) {
-                    int budget = max_det - kept;
-                    for (int w = 0; w < NMS_TILE_WORDS; ++w) {
-                        u64 kw = ((u64)S.keep32[cur][2 * w + 1] << 32) | S.keep32[cur][2 * w];
-                        int c = __popcll(kw);
-                        while (c > budget) { kw &= ~(1ull << (63 - __clzll((long long)kw))); --c; }
-                        budget -= c;
-                        S.keepmask[w] = kw;
-                    }
-                }
-            }
-            __syncthreads();
-            // E: append the kept ones (in order) to the kept list and to the output
-            int added = 0;
+            int cur = 0;
+            for (;;) {
+                const unsigned* K = S.keep32[cur];
+                u64 hit = 0ull;
 #pragma unroll
-            for (int w = 0; w < NMS_TILE_WORDS; ++w) added += __popcll(S.keepmask[w]);
-            if (tid < nt) {
-                const int w = tid >> 6, bit = tid & 63;
-                if ((S.keepmask[w] >> bit) & 1ull) {
-                    int pos = kept + __popcll(S.keepmask[w] & ((1ull << bit) - 1ull));
-                    for (int ww = 0; ww < w; ++ww) pos += __popcll(S.keepmask[ww]);
-                    kbox[pos] = S.tbox[tid];
-                    karea[pos] = S.tarea[tid];
-                    kcode[pos] = S.tcode[tid];
-                    const float4 r = S.traw[tid];
-                    float* o = dets + (size_t)pos * 6;  // general.py:474 rows (x1,y1,x2,y2,conf,cls)
-                    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
-                    o[4] = S.tscore[tid];
-                    o[5] = (float)S.tcls[tid];
-                }
+                for (int w = 0; w < NMS_TILE_WORDS; ++w) hit |= m[w] & (((u64)K[2 * w + 1] << 32) | (u64)K[2 * w]);
+                const bool kj = !dead && hit == 0ull;
+                const unsigned nw = __ballot_sync(0xffffffffu, kj);
+                int changed = 0;
+                if (lane == 0) { S.keep32[cur ^ 1][wid] = nw; changed = (nw != K[wid]); }
+                cur ^= 1;
+                if (!__syncthreads_or(changed)) break;
             }
-            kept += added;
+            // E: the first `budget` kept candidates (greedy stops at max_det, general.py:465) are appended,
+            //    in order, to the kept list and to the output
+            {
+                const unsigned* K = S.keep32[cur];
+                int before = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < NMS_THREADS / 32; ++w) {
+                    const int c = __popc(K[w]);
+                    if (w < wid) before += c;
+                    total += c;
+                }
+                const bool mine = (K[wid] >> lane) & 1u;
+                const int pos = kept + before + __popc(K[wid] & ((1u << lane) - 1u));
+                if (mine && pos < max_det) {
+                    kbox[pos] = box;
+                    karea[pos] = area;
+                    float* o = dets + (size_t)pos * 6;  // general.py:474 rows (x1,y1,x2,y2,conf,cls)
+                    o[0] = raw.x; o[1] = raw.y; o[2] = raw.z; o[3] = raw.w;
+                    o[4] = score;
+                    o[5] = (float)cls;
+                    if (code < 0) S.kept_wild = 1;
+                    if (max_det <= NMS_KEPT_SMEM) {  // chain the box into its class bucket (any order is fine)
+                        const int old = atomicExch(&S.khead[cls & (NMS_BUCKETS - 1)], pos);
+                        S.knext_s[pos] = old;
+                    }
+                }
+                kept = min(kept + total, max_det);
+            }
             __syncthreads();
+            kept_wild = kept_wild || (S.kept_wild != 0);
         }
     };
 
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
     if (max_det <= NMS_KEPT_SMEM) return 0;
-    return (size_t)T * B * max_det * 6 * sizeof(float);
+    return (size_t)T * B * max_det * 5 * sizeof(float);
 }
 
 template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParams& P, cudaStream_t stream) {

@@ -138,6 +138,24 @@ def test_nms_constant_scores_massive_ties(ops, dtype):
         _assert_rows_equal(got, want, str(kw))
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("multi", [False, True])
+def test_nms_wild_boxes_outside_class_window(ops, dtype, multi):
+    """Boxes far outside [0, max_wh): class-offset boxes of different classes DO overlap there
+    (reference general.py:462-463 quirk), so the per-class shortcut must switch itself off."""
+    from cerberusdet_b200.nms import non_max_suppression
+    from oracle import ref_port as rp
+
+    pred = synth_prediction(2, 6, 1500, seed=31, dtype=torch.float32, regime="clusters", imgsz=9000.0)
+    pred[:, 0:2] -= 1500.0  # centres in [-1500, 7500]: some boxes below -960, some above 6720
+    pred[1, 0:2, ::3] += 7680.0  # image 1: a third of the boxes shifted by exactly one class gap
+    pred = pred.to(dtype)
+    kw = dict(conf_thres=0.05, iou_thres=0.5, multi_label=multi, max_det=300)
+    want = rp.nms_port(pred, greedy="c", **kw)
+    got = non_max_suppression(_dev(pred), **kw)
+    _assert_rows_equal(got, want, "wild")
+
+
 def _truncation_prediction(dtype, seed=3):
     """> 30000 multi-label candidates, nearly all inside one heavy cluster (suppressed by its top box)
     plus isolated boxes whose scores straddle the rank-30000 cut: the kept set is sensitive to the exact
