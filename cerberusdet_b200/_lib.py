@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcerb_post.so")
+LIB_PATH = os.environ.get("CERB_LIB") or os.path.join(_HERE, "libcerb_post.so")  # CERB_LIB: tools/ only
 
 CERB_F16, CERB_F32 = 0, 1
 CERB_EINVAL, CERB_ECUDA, CERB_ENOSPC = -1, -2, -3

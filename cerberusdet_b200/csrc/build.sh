@@ -2,7 +2,7 @@
 # Build libcerb_post.so in-tree for sm_100a.  Usage: sh cerberusdet_b200/csrc/build.sh [extra nvcc flags]
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
-OUT="$HERE/../libcerb_post.so"
+OUT="${CERB_OUT:-$HERE/../libcerb_post.so}"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
      -Xcompiler -fPIC -shared "$@" \
      -o "$OUT" "$HERE/decode.cu" "$HERE/nms.cu" "$HERE/api.cu"

@@ -36,6 +36,29 @@
 
 typedef unsigned long long u64;
 
+// Optional phase timers (-DNMS_PROFILE, tools/ only): block 0 accumulates clock64() deltas per phase.
+#ifdef NMS_PROFILE
+__device__ unsigned long long g_nms_prof[16];
+#define PROF_DECL long long prof_t = clock64();
+#define PROF(slot)                                                        \
+    do {                                                                  \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                        \
+            const long long now = clock64();                              \
+            g_nms_prof[slot] += (unsigned long long)(now - prof_t);       \
+            prof_t = now;                                                 \
+        }                                                                 \
+    } while (0)
+extern "C" int cerb_debug_read_profile(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_nms_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_nms_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define PROF_DECL
+#define PROF(slot) do {} while (0)
+#endif
+
 struct __align__(16) NmsSmem {
     unsigned g0[NMS_BINS + 8];   // level-0: G0[d] = #keys with digit >= d (histogram units); G0[4096] = 0
     unsigned g1[NMS_BINS + 8];   // scratch for deeper levels
@@ -87,12 +110,61 @@ template <typename T> struct ScoreVec {
 
 #define SCAN_UNROLL 4
 
+// Per-dtype form of the score-bit range [sb_lo, sb_hi] (positive floats: bit order == value order).
+template <typename T> struct RangeBounds;
+template <> struct RangeBounds<float> { unsigned lo, span; };
+template <> struct RangeBounds<__half> { __half2 lo2, hi2; };
+template <typename T> __device__ __forceinline__ RangeBounds<T> make_range_bounds(unsigned sb_lo, unsigned sb_hi);
+template <> __device__ __forceinline__ RangeBounds<float> make_range_bounds<float>(unsigned sb_lo, unsigned sb_hi) {
+    RangeBounds<float> r;
+    r.lo = sb_lo;
+    r.span = sb_hi - sb_lo;
+    return r;
+}
+template <> __device__ __forceinline__ RangeBounds<__half> make_range_bounds<__half>(unsigned sb_lo, unsigned sb_hi) {
+    // smallest half >= lo and largest half <= hi: for half data  lo <= float(s) <= hi  <=>  lo_h <= s <= hi_h
+    RangeBounds<__half> r;
+    r.lo2 = __half2half2(__float2half_ru(__uint_as_float(sb_lo)));
+    r.hi2 = __half2half2(__float2half_rd(__uint_as_float(sb_hi)));
+    return r;
+}
+// bit k set iff element k of the vector has its score bits in [sb_lo, sb_hi]
+template <typename T>
+__device__ __forceinline__ unsigned range_hits(const ScoreVec<T>& v, unsigned sb_lo, unsigned sb_hi, const RangeBounds<T>& rb);
+template <>
+__device__ __forceinline__ unsigned range_hits<float>(const ScoreVec<float>& v, unsigned, unsigned, const RangeBounds<float>& rb) {
+    unsigned h = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h |= ((__float_as_uint(v.e[k]) - rb.lo) <= rb.span ? 1u : 0u) << k;
+    return h;
+}
+template <>
+__device__ __forceinline__ unsigned range_hits<__half>(const ScoreVec<__half>& v, unsigned, unsigned, const RangeBounds<__half>& rb) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v.raw);
+    unsigned m[4], any = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { m[p] = __hge2_mask(h2[p], rb.lo2) & __hle2_mask(h2[p], rb.hi2); any |= m[p]; }
+    if (!any) return 0u;
+    unsigned h = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) h |= ((m[p] & 1u) | ((m[p] >> 15) & 2u)) << (2 * p);
+    return h;
+}
+
 template <typename T, bool MULTI, typename F>
 __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, int nc, int A, float thr,
-                                                   const NmsParams& P, F f, const unsigned vstride = 1) {
-    // vstride > 1 visits only every vstride-th 16-byte vector (multi-label vector path only): used for the
-    // *estimating* histogram; every exact pass uses vstride == 1.
+                                                   const NmsParams& P, F f, unsigned sb_lo = 0u,
+                                                   unsigned sb_hi = 0x7F800000u, const unsigned vstride = 1) {
+    // Only candidates whose score bits lie in [sb_lo, sb_hi] are reported (a whole vector is rejected with
+    // a few packed compares).  vstride > 1 visits only every vstride-th 16-byte vector (multi-label vector
+    // path only): used for the *estimating* histogram; every exact pass uses vstride == 1.
     constexpr int V = ScoreVec<T>::V;
+    {   // fold the strict "score > conf_thres" (thr >= 0, so it is a bit-pattern compare) into the range
+        const unsigned tb = __float_as_uint(thr) + 1u;
+        sb_lo = sb_lo > tb ? sb_lo : tb;
+        sb_hi = sb_hi < 0x7F800000u ? sb_hi : 0x7F800000u;  // excludes NaN
+    }
+    if (sb_lo > sb_hi) return;
     const T* __restrict__ sc = img + (size_t)4 * A;
     const bool vec_ok = (A % V == 0) && ((reinterpret_cast<uintptr_t>(sc) & 15) == 0);
     const bool filt = P.use_class_filter != 0;
@@ -100,6 +172,7 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
         if (vec_ok) {
             const unsigned nvec = (unsigned)(((u64)nc * (u64)A) / V);
             const unsigned nvis = (nvec + vstride - 1) / vstride;  // vectors visited
+            const RangeBounds<T> rb = make_range_bounds<T>(sb_lo, sb_hi);
             for (unsigned q0 = threadIdx.x; q0 < nvis; q0 += NMS_THREADS * SCAN_UNROLL) {
                 ScoreVec<T> v[SCAN_UNROLL];
 #pragma unroll
@@ -111,16 +184,15 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
                 for (int u = 0; u < SCAN_UNROLL; ++u) {
                     const unsigned q = q0 + u * NMS_THREADS;
                     if (q >= nvis) break;
-                    const unsigned i = q * vstride;
-                    const unsigned e0 = i * V;
+                    const unsigned hits = range_hits<T>(v[u], sb_lo, sb_hi, rb);
+                    if (!hits) continue;
+                    const unsigned e0 = q * vstride * V;
                     const unsigned c = e0 / (unsigned)A;
                     const unsigned a0 = e0 - c * (unsigned)A;
                     if (filt && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
 #pragma unroll
-                    for (int k = 0; k < V; ++k) {
-                        const float s = to_f32<T>(v[u].e[k]);
-                        if (s > thr) f(make_sbits(s), (int)(a0 + k), (int)c);
-                    }
+                    for (int k = 0; k < V; ++k)
+                        if ((hits >> k) & 1u) f(make_sbits(to_f32<T>(v[u].e[k])), (int)(a0 + k), (int)c);
                 }
             }
         } else {
@@ -128,8 +200,8 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
                 if (filt && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
                 const T* __restrict__ row = sc + (size_t)c * A;
                 for (int a = threadIdx.x; a < A; a += NMS_THREADS) {
-                    const float s = to_f32<T>(__ldg(row + a));
-                    if (s > thr) f(make_sbits(s), a, c);
+                    const unsigned sb = make_sbits(to_f32<T>(__ldg(row + a)));
+                    if (sb - sb_lo <= sb_hi - sb_lo) f(sb, a, c);
                 }
             }
         }
@@ -170,9 +242,10 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
                 }
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
-                    if (best[k] > thr) {
+                    const unsigned sb = make_sbits(best[k]);
+                    if (sb - sb_lo <= sb_hi - sb_lo) {
                         if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
-                        f(make_sbits(best[k]), i * V + k, bc[k]);
+                        f(sb, i * V + k, bc[k]);
                     }
                 }
             }
@@ -184,9 +257,10 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
                     const float s = to_f32<T>(__ldg(sc + (size_t)c * A + a));
                     if (s > best) { best = s; bc = c; }  // lowest index wins ties (torch.max)
                 }
-                if (best > thr) {
+                const unsigned sb = make_sbits(best);
+                if (sb - sb_lo <= sb_hi - sb_lo) {
                     if (filt && !((P.class_mask[bc >> 5] >> (bc & 31)) & 1u)) continue;
-                    f(make_sbits(best), a, bc);
+                    f(sb, a, bc);
                 }
             }
         }
@@ -233,6 +307,64 @@ __device__ __forceinline__ int find_digit(const unsigned* G, int hi, unsigned ba
     return lo;
 }
 
+// Bitonic sort (descending) of E * NMS_THREADS 64-bit keys held in shared memory.  Element i = e * 512 + tid
+// lives in register e of thread tid: partners at distance j < 32 are reached with warp shuffles, at
+// 32 <= j < 512 through shared memory, at j >= 512 inside the thread -- 10 block barriers pairs instead
+// of one per network stage.
+template <int E> __device__ __forceinline__ void block_sort_desc(u64* keys) {
+    const unsigned tid = threadIdx.x;
+    u64 r[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = keys[e * NMS_THREADS + tid];
+    for (unsigned k = 2; k <= (unsigned)E * NMS_THREADS; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            if (j >= NMS_THREADS) {
+                const int je = j / NMS_THREADS;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int pe = e ^ je;
+                    if (pe > e) {
+                        const unsigned i = e * NMS_THREADS + tid;
+                        const bool desc = ((i & k) == 0);
+                        const u64 x = r[e], y = r[pe];
+                        if (desc ? (x < y) : (x > y)) { r[e] = y; r[pe] = x; }
+                    }
+                }
+            } else if (j >= 32) {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) keys[e * NMS_THREADS + tid] = r[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned i = e * NMS_THREADS + tid;
+                    const u64 y = keys[i ^ j];
+                    const bool lower = (i & j) == 0;          // i < partner
+                    const bool desc = ((i & k) == 0);
+                    const bool take_max = (lower == desc);    // this slot keeps the larger key
+                    const u64 x = r[e];
+                    r[e] = take_max ? (x > y ? x : y) : (x < y ? x : y);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned i = e * NMS_THREADS + tid;
+                    const u64 x = r[e];
+                    const u64 y = __shfl_xor_sync(0xffffffffu, x, j);
+                    const bool lower = (i & j) == 0;
+                    const bool desc = ((i & k) == 0);
+                    const bool take_max = (lower == desc);
+                    r[e] = take_max ? (x > y ? x : y) : (x < y ? x : y);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) keys[e * NMS_THREADS + tid] = r[e];
+    __syncthreads();
+}
+
 template <typename T, bool MULTI>
 __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -270,6 +402,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     // ESTIMATE built from every hstride-th score vector: chunk boundaries only steer how much is
     // gathered at once; what a chunk contains, its order and every count that matters (collect)
     // are exact.  A chunk that turns out too large switches the segment to the exact histogram.
+    PROF_DECL
     const unsigned max_nms = (unsigned)max(P.max_nms, 0);
     unsigned hstride = 1;
     if (MULTI && P.hist_sample > 1) {
@@ -280,13 +413,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
         __syncthreads();
         for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int, int) {
-            const unsigned d = sb >> 20;
-            if (d < below_digit) atomicAdd(&S.g0[d], 1u);
-        }, stride);
+            atomicAdd(&S.g0[sb >> 20], 1u);
+        }, 0u, below_digit >= 2048u ? 0x7F800000u : (below_digit << 20) - 1u, stride);
         __syncthreads();
         suffix_scan(S.g0, S.warp_tot);
     };
+    PROF(0);  // setup
     build_hist(hstride, NMS_BINS);
+    PROF(1);  // first histogram
 
     unsigned consumed = 0;
     int kept = 0;
@@ -294,24 +428,20 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
 
     // -------- consume the sorted chunk in S.keys[0..n) (first `take` entries) ; returns updated kept
     auto consume_chunk = [&](unsigned n, unsigned take) {
-        // bitonic sort, descending, padded with zeros (keys are never 0)
-        unsigned n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (unsigned i = n + tid; i < n2; i += NMS_THREADS) S.keys[i] = 0ull;
-        __syncthreads();
-        for (unsigned k = 2; k <= n2; k <<= 1) {
-            for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned i = tid; i < n2; i += NMS_THREADS) {
-                    const unsigned ixj = i ^ j;
-                    if (ixj > i) {
-                        const u64 x = S.keys[i], y = S.keys[ixj];
-                        const bool desc = ((i & k) == 0);
-                        if (desc ? (x < y) : (x > y)) { S.keys[i] = y; S.keys[ixj] = x; }
-                    }
-                }
-                __syncthreads();
+        // bitonic sort, descending, padded with zeros (keys are never 0); see block_sort_desc
+        {
+            unsigned n2 = NMS_THREADS;
+            while (n2 < n) n2 <<= 1;
+            for (unsigned i = n + tid; i < n2; i += NMS_THREADS) S.keys[i] = 0ull;
+            __syncthreads();
+            switch (n2 / NMS_THREADS) {
+                case 1: block_sort_desc<1>(S.keys); break;
+                case 2: block_sort_desc<2>(S.keys); break;
+                case 4: block_sort_desc<4>(S.keys); break;
+                default: block_sort_desc<8>(S.keys); break;
             }
         }
+        PROF(3);  // sort
         // tiles: one candidate per thread
         for (unsigned t0 = 0; t0 < take && kept < max_det; t0 += NMS_TILE) {
             const int nt = (int)min((unsigned)NMS_TILE, take - t0);
@@ -354,6 +484,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             S.tarea[tid] = area;
             S.tcode[tid] = dead ? -2 : code;  // -2: padding, never equal to a class
             __syncthreads();
+            PROF(4);  // tile A (gather)
             // Per-class chains are valid while every box involved is tame (see the class shortcut above).
             const bool fast = shortcut && !S.tile_wild && !kept_wild;
             int prev = -1;
@@ -377,28 +508,31 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             }
             S.tdead[tid] = dead ? 1 : 0;
             __syncthreads();
+            PROF(5);  // tile B (prev chain + kept list)
             // C: m[w] = bits of the earlier candidates i in word w (alive) that would suppress this one
-            u64 m[NMS_TILE_WORDS];
-#pragma unroll
-            for (int w = 0; w < NMS_TILE_WORDS; ++w) m[w] = 0ull;
+            u64 m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0;
+#define NMS_SETBIT(i)                                        \
+    do {                                                     \
+        const u64 bit_ = 1ull << ((i) & 63);                 \
+        switch ((i) >> 6) {                                  \
+            case 0: m0 |= bit_; break;                       \
+            case 1: m1 |= bit_; break;                       \
+            case 2: m2 |= bit_; break;                       \
+            case 3: m3 |= bit_; break;                       \
+            case 4: m4 |= bit_; break;                       \
+            case 5: m5 |= bit_; break;                       \
+            case 6: m6 |= bit_; break;                       \
+            default: m7 |= bit_; break;                      \
+        }                                                    \
+    } while (0)
             if (!dead) {
                 if (fast) {
                     for (int i = prev; i >= 0; i = S.tprev[i]) {
-                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) {
-                            const u64 bit = 1ull << (i & 63);
-#pragma unroll
-                            for (int w = 0; w < NMS_TILE_WORDS; ++w)
-                                if (w == (i >> 6)) m[w] |= bit;
-                        }
+                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
                     }
                 } else {
                     for (int i = 0; i < tid; ++i) {
-                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) {
-                            const u64 bit = 1ull << (i & 63);
-#pragma unroll
-                            for (int w = 0; w < NMS_TILE_WORDS; ++w)
-                                if (w == (i >> 6)) m[w] |= bit;
-                        }
+                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
                     }
                 }
             }
@@ -407,22 +541,42 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 if (lane == 0) S.keep32[0][wid] = al;
             }
             __syncthreads();
+            PROF(6);  // tile C (pairwise)
             // D: greedy result as the fixpoint of  keep[j] = alive[j] && no kept earlier i suppresses j.
-            //    It is unique (keep[j] depends only on lower indices) and after r rounds the first r
-            //    candidates are final, so the loop ends in <= nt rounds -- in practice a handful.
+            //    It is unique (keep[j] depends only on lower indices).  Every block round lets each warp
+            //    settle its own 32 candidates to their fixpoint given the other warps' current words, so
+            //    after round r the first r warps are final: <= 16 rounds, in practice 2-3.
             int cur = 0;
-            for (;;) {
-                const unsigned* K = S.keep32[cur];
-                u64 hit = 0ull;
+            {
+                const int myw = wid >> 1;          // 64-bit word holding this warp's 32 candidates
+                const bool upper = (wid & 1) != 0; // which half of it
+                const u64 mw[NMS_TILE_WORDS] = {m0, m1, m2, m3, m4, m5, m6, m7};
+                u64 mown = 0ull;
 #pragma unroll
-                for (int w = 0; w < NMS_TILE_WORDS; ++w) hit |= m[w] & (((u64)K[2 * w + 1] << 32) | (u64)K[2 * w]);
-                const bool kj = !dead && hit == 0ull;
-                const unsigned nw = __ballot_sync(0xffffffffu, kj);
-                int changed = 0;
-                if (lane == 0) { S.keep32[cur ^ 1][wid] = nw; changed = (nw != K[wid]); }
-                cur ^= 1;
-                if (!__syncthreads_or(changed)) break;
+                for (int w = 0; w < NMS_TILE_WORDS; ++w)
+                    if (w == myw) mown = mw[w];
+                for (;;) {
+                    const unsigned* K = S.keep32[cur];
+                    u64 others = 0ull;
+#pragma unroll
+                    for (int w = 0; w < NMS_TILE_WORDS; ++w)
+                        if (w != myw) others |= mw[w] & (((u64)K[2 * w + 1] << 32) | (u64)K[2 * w]);
+                    const unsigned sibling = K[wid ^ 1];
+                    unsigned mine = K[wid];
+                    for (;;) {  // warp-local settle
+                        const u64 own = upper ? (((u64)mine << 32) | (u64)sibling) : (((u64)sibling << 32) | (u64)mine);
+                        const bool kj = !dead && (others | (mown & own)) == 0ull;
+                        const unsigned nw = __ballot_sync(0xffffffffu, kj);
+                        if (nw == mine) break;
+                        mine = nw;
+                    }
+                    int changed = 0;
+                    if (lane == 0) { S.keep32[cur ^ 1][wid] = mine; changed = (mine != K[wid]); }
+                    cur ^= 1;
+                    if (!__syncthreads_or(changed)) break;
+                }
             }
+            PROF(7);  // tile D (fixpoint)
             // E: the first `budget` kept candidates (greedy stops at max_det, general.py:465) are appended,
             //    in order, to the kept list and to the output
             {
@@ -453,6 +607,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             }
             __syncthreads();
             kept_wild = kept_wild || (S.kept_wild != 0);
+            PROF(8);  // tile E (append)
         }
     };
 
@@ -462,17 +617,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         __syncthreads();
         const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
         for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int a, int c) {
-            if (sb >= sb_lo && sb <= sb_hi) {
-                const u64 key = make_key(sb, (unsigned)(a * nc + c));
-                if (key >= lo && key < hi) {
-                    const unsigned p = atomicAdd(&S.counter, 1u);
-                    if (p < NMS_CAP) S.keys[p] = key;
-                }
+            const u64 key = make_key(sb, (unsigned)(a * nc + c));
+            if (key >= lo && key < hi) {
+                const unsigned p = atomicAdd(&S.counter, 1u);
+                if (p < NMS_CAP) S.keys[p] = key;
             }
-        });
+        }, sb_lo, sb_hi);
         __syncthreads();
         const unsigned n = S.counter;
         __syncthreads();
+        PROF(2);  // collect (and chunk search before it)
         return n;
     };
 
@@ -489,11 +643,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 __syncthreads();
                 const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
                 for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int a, int c) {
-                    if (sb >= sb_lo && sb <= sb_hi) {
-                        const u64 key = make_key(sb, (unsigned)(a * nc + c));
-                        if (key >= lo && key < hi) atomicAdd(&S.g1[level_digit(key, lvl)], 1u);
-                    }
-                });
+                    const u64 key = make_key(sb, (unsigned)(a * nc + c));
+                    if (key >= lo && key < hi) atomicAdd(&S.g1[level_digit(key, lvl)], 1u);
+                }, sb_lo, sb_hi);
                 __syncthreads();
                 suffix_scan(S.g1, S.warp_tot);
                 const unsigned tot = S.g1[0];
@@ -563,10 +715,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         consume_chunk(n, take);
         consumed += take;
         hi0 = lo0;
-        target = min(target * 2u, cap);
+        target = min(target * 4u, cap);
     }
 
     if (tid == 0) P.counts[seg] = kept;
+    PROF(9);  // rest
+#ifdef NMS_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g_nms_prof[10] += 1; g_nms_prof[11] += consumed; }
+#endif
 }
 
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
