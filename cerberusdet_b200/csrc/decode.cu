@@ -98,10 +98,16 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_consta
 
     const int hw = P.hw[level];
     const int nvec = hw / VEC;
+    // Vectors per image are padded to a whole number of 64-anchor score-summary groups so that the lanes of
+    // one group are always LPG consecutive, aligned lanes (see the summary below).
+    constexpr int LPG = (CERB_SUM_GROUP / VEC) <= 32 ? (CERB_SUM_GROUP / VEC) : 32;
+    const int nvecp = P.row_nvecp[row];
     const int item = vblk * DEC_THREADS + threadIdx.x;
-    if (item >= P.B * nvec) return;
-    const int b = item / nvec;
-    const int a0 = (item - b * nvec) * VEC;  // first anchor inside the level
+    const int b = item / nvecp;
+    const int v = item - b * nvecp;
+    const bool valid = (b < P.B) && (v < nvec);
+    if (part < 2 && !valid) return;
+    const int a0 = v * VEC;  // first anchor inside the level
 
     const int nc = P.nc[task];
     const int no = 4 * CERB_REG_MAX + nc;
@@ -131,34 +137,60 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_consta
         store_pack<T, VEC>(out + (size_t)part * P.A, oc);
         store_pack<T, VEC>(out + (size_t)(part + 2) * P.A, os);
     } else {
-        // class scores: sigmoid (yolo.py:99)
+        // class scores: sigmoid (yolo.py:99).  Optionally also the score summary: the maximum score of each
+        // (class, 64-anchor group), which lets the NMS kernel skip the groups that cannot hold a candidate.
         const int c0 = (part - 2) * CLS_CHUNK;
         const int c1 = min(nc, c0 + CLS_CHUNK);
         const T* __restrict__ cin = in + (size_t)(4 * CERB_REG_MAX) * hw;
         T* __restrict__ cout = out + (size_t)4 * P.A;
+        T* __restrict__ smax = nullptr;
+        if (CERB_SUM_GROUP % VEC == 0 && CERB_SUM_GROUP / VEC <= 32 && P.smax[task] != nullptr && b < P.B)
+            smax = reinterpret_cast<T*>(P.smax[task]) + (size_t)b * nc * P.G + P.goff[level] + v / LPG;
+        const bool writer = (threadIdx.x % LPG) == 0;
         int c = c0;
         for (; c + 4 <= c1; c += 4) {
-            Pack<T, VEC> v[4];
+            Pack<T, VEC> vv[4];
+            if (valid) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
+                for (int u = 0; u < 4; ++u) vv[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                float mx = -INFINITY;
+                if (valid) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float x = to_f32<T>(v[u].e[i]);
-                    v[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                    for (int i = 0; i < VEC; ++i) {
+                        const float x = to_f32<T>(vv[u].e[i]);
+                        vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                        mx = fmaxf(mx, to_f32<T>(vv[u].e[i]));
+                    }
+                    store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, vv[u]);
                 }
-                store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, v[u]);
+                if (P.smax[task] != nullptr) {  // block-uniform
+#pragma unroll
+                    for (int o = 1; o < LPG; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (smax != nullptr && writer && v < nvec) smax[(size_t)(c + u) * P.G] = from_f32<T>(mx);
+                }
             }
         }
         for (; c < c1; ++c) {
-            Pack<T, VEC> v = load_pack<T, VEC>(cin + (size_t)c * hw);
+            Pack<T, VEC> v1;
+            float mx = -INFINITY;
+            if (valid) {
+                v1 = load_pack<T, VEC>(cin + (size_t)c * hw);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float x = to_f32<T>(v.e[i]);
-                v.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                for (int i = 0; i < VEC; ++i) {
+                    const float x = to_f32<T>(v1.e[i]);
+                    v1.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                    mx = fmaxf(mx, to_f32<T>(v1.e[i]));
+                }
+                store_pack<T, VEC>(cout + (size_t)c * P.A, v1);
             }
-            store_pack<T, VEC>(cout + (size_t)c * P.A, v);
+            if (P.smax[task] != nullptr) {
+#pragma unroll
+                for (int o = 1; o < LPG; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (smax != nullptr && writer && v < nvec) smax[(size_t)c * P.G] = from_f32<T>(mx);
+            }
         }
     }
 }
@@ -168,7 +200,11 @@ template <typename T, int VEC> static cudaError_t launch_decode_t(DecodeParams& 
     for (int t = 0; t < P.T; ++t)
         for (int l = 0; l < P.L; ++l) {
             const int row = t * P.L + l;
-            const long items = (long)P.B * (P.hw[l] / VEC);
+            constexpr int LPG = (CERB_SUM_GROUP / VEC) <= 32 ? (CERB_SUM_GROUP / VEC) : 32;
+            const int nvec = P.hw[l] / VEC;
+            const int nvecp = (nvec + LPG - 1) / LPG * LPG;
+            P.row_nvecp[row] = nvecp;
+            const long items = (long)P.B * nvecp;
             const int bpp = (int)((items + DEC_THREADS - 1) / DEC_THREADS);
             const int parts = 2 + (P.nc[t] + CLS_CHUNK - 1) / CLS_CHUNK;
             P.row_start[row] = blocks;

@@ -70,7 +70,7 @@ struct __align__(16) NmsSmem {
     unsigned keep32[2][NMS_TILE / 32];
     unsigned char tdead[NMS_TILE];
     unsigned warp_tot[NMS_THREADS / 32];
-    unsigned counter;
+    unsigned counter, nhits;
     int tile_wild, kept_wild;
     int khead[NMS_BUCKETS];      // newest kept box of each class bucket, or -1
     int knext_s[NMS_KEPT_SMEM];  // next kept box of the same bucket
@@ -267,6 +267,95 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
     }
 }
 
+// ---- the same enumeration guided by the score summary (max score of every (class, 64-anchor group),
+// written by the decode kernel): only the groups whose maximum reaches sb_lo are read at all.  `hits` is a
+// shared-memory scratch list of NMS_BINS entries.  with_scores == false only visits the summary itself and
+// reports one pseudo-candidate per group (its maximum) -- that is the estimating histogram.
+template <typename T, bool MULTI, bool WITH_SCORES, typename F>
+__device__ __forceinline__ void for_each_candidate_summary(const T* __restrict__ img, const T* __restrict__ smax,
+                                                           int nc, int A, float thr, const NmsParams& P, F f,
+                                                           unsigned sb_lo, unsigned sb_hi, unsigned* hits,
+                                                           unsigned* nhits) {
+    constexpr int V = ScoreVec<T>::V;
+    constexpr int VPG = CERB_SUM_GROUP / V;  // vectors per group
+    const T* __restrict__ sc = img + (size_t)4 * A;
+    const unsigned G = (unsigned)P.G;
+    const bool filt = P.use_class_filter != 0;
+    {
+        const unsigned tb = __float_as_uint(thr) + 1u;
+        sb_lo = sb_lo > tb ? sb_lo : tb;
+        sb_hi = sb_hi < 0x7F800000u ? sb_hi : 0x7F800000u;
+    }
+    if (sb_lo > sb_hi) return;
+    const RangeBounds<T> rb = make_range_bounds<T>(sb_lo, sb_hi);
+    const unsigned entries = MULTI ? (unsigned)nc * G : G;
+    for (unsigned slab = 0; slab < entries; slab += NMS_BINS) {
+        __syncthreads();
+        if (threadIdx.x == 0) *nhits = 0;
+        __syncthreads();
+        const unsigned slab_end = min(entries, slab + (unsigned)NMS_BINS);
+        for (unsigned e = slab + threadIdx.x; e < slab_end; e += NMS_THREADS) {
+            unsigned sbm;
+            if (MULTI) {
+                if (filt) { const unsigned c = e / G; if (!((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue; }
+                sbm = make_sbits(to_f32<T>(__ldg(smax + e)));
+            } else {
+                float mx = to_f32<T>(__ldg(smax + e));
+                for (int c = 1; c < nc; ++c) mx = fmaxf(mx, to_f32<T>(__ldg(smax + (size_t)c * G + e)));
+                sbm = make_sbits(mx);
+            }
+            if (sbm >= sb_lo && sbm <= 0x7F800000u) {
+                if (WITH_SCORES) hits[atomicAdd(nhits, 1u)] = e;
+                else if (sbm <= sb_hi) f(sbm, 0, 0);
+            }
+        }
+        if (!WITH_SCORES) continue;
+        __syncthreads();
+        const unsigned items = *nhits * VPG;
+        for (unsigned it = threadIdx.x; it < items; it += NMS_THREADS) {
+            const unsigned e = hits[it / VPG], j = it % VPG;
+            const unsigned c = MULTI ? e / G : 0u, g = MULTI ? e - c * G : e;
+            int l = 0;
+            while (l + 1 < P.L && g >= (unsigned)P.lvl_goff[l + 1]) ++l;
+            const unsigned a_in = (g - (unsigned)P.lvl_goff[l]) * CERB_SUM_GROUP + j * V;
+            if (a_in >= (unsigned)P.lvl_hw[l]) continue;
+            const unsigned a_s = (unsigned)P.lvl_aoff[l] + a_in;
+            if (MULTI) {
+                ScoreVec<T> v;
+                v.raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)c * A + a_s));
+                const unsigned h = range_hits<T>(v, sb_lo, sb_hi, rb);
+                if (!h) continue;
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if ((h >> k) & 1u) f(make_sbits(to_f32<T>(v.e[k])), (int)(a_s + k), (int)c);
+            } else {
+                float best[V];
+                int bc[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bc[k] = 0; }
+                for (int cc = 0; cc < nc; ++cc) {
+                    ScoreVec<T> v;
+                    v.raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)cc * A + a_s));
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float sv = to_f32<T>(v.e[k]);
+                        if (cc == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc; }  // lowest index wins ties
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const unsigned sb = make_sbits(best[k]);
+                    if (sb - sb_lo <= sb_hi - sb_lo) {
+                        if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
+                        f(sb, (int)(a_s + k), bc[k]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ int level_shift(int lvl) { return lvl < 5 ? 52 - 12 * lvl : 0; }
 __device__ __forceinline__ unsigned level_digit(u64 key, int lvl) {
     return lvl < 5 ? (unsigned)(key >> (52 - 12 * lvl)) & 0xFFFu : (unsigned)key & 0xFu;
@@ -404,11 +493,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     // are exact.  A chunk that turns out too large switches the segment to the exact histogram.
     PROF_DECL
     const unsigned max_nms = (unsigned)max(P.max_nms, 0);
-    unsigned hstride = 1;
-    if (MULTI && P.hist_sample > 1) {
+    const T* __restrict__ smax =
+        P.smax[task] ? reinterpret_cast<const T*>(P.smax[task]) + (size_t)b * nc * P.G : nullptr;
+    unsigned hstride = 1;  // > 1: the histogram is a 1/hstride sample
+    if (!smax && MULTI && P.hist_sample > 1) {
         const u64 nvec = ((u64)nc * (u64)A) / ScoreVec<T>::V;
         if (nvec >= 8192 && (A % ScoreVec<T>::V) == 0) hstride = (unsigned)P.hist_sample;
     }
+    bool exact = (hstride == 1) && !smax;  // histogram counts every candidate
     auto build_hist = [&](unsigned stride, unsigned below_digit) {
         for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
         __syncthreads();
@@ -418,8 +510,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         __syncthreads();
         suffix_scan(S.g0, S.warp_tot);
     };
+    // with a score summary the histogram counts GROUPS by their maximum: a lower bound on the candidates of
+    // every digit range (each group contributes at least its maximum), which is all the chunk search needs
+    auto build_hist_summary = [&]() {
+        for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
+        __syncthreads();
+        for_each_candidate_summary<T, MULTI, false>(img, smax, nc, A, thr, P, [&](unsigned sb, int, int) {
+            atomicAdd(&S.g0[sb >> 20], 1u);
+        }, 0u, 0x7F800000u, S.g1, &S.nhits);
+        __syncthreads();
+        suffix_scan(S.g0, S.warp_tot);
+    };
     PROF(0);  // setup
-    build_hist(hstride, NMS_BINS);
+    if (smax) build_hist_summary(); else build_hist(hstride, NMS_BINS);
     PROF(1);  // first histogram
 
     unsigned consumed = 0;
@@ -616,13 +719,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         if (tid == 0) S.counter = 0;
         __syncthreads();
         const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
-        for_each_candidate<T, MULTI>(img, nc, A, thr, P, [&](unsigned sb, int a, int c) {
+        auto put = [&](unsigned sb, int a, int c) {
             const u64 key = make_key(sb, (unsigned)(a * nc + c));
             if (key >= lo && key < hi) {
                 const unsigned p = atomicAdd(&S.counter, 1u);
                 if (p < NMS_CAP) S.keys[p] = key;
             }
-        }, sb_lo, sb_hi);
+        };
+        if (smax) for_each_candidate_summary<T, MULTI, true>(img, smax, nc, A, thr, P, put, sb_lo, sb_hi, S.g1, &S.nhits);
+        else for_each_candidate<T, MULTI>(img, nc, A, thr, P, put, sb_lo, sb_hi);
         __syncthreads();
         const unsigned n = S.counter;
         __syncthreads();
@@ -684,18 +789,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     while (hi0 > 0 && consumed < max_nms && kept < max_det) {
         const unsigned base = S.g0[hi0];
         const unsigned rem_s = S.g0[0] - base;  // candidates left below hi0, in histogram units
-        if (hstride == 1 && rem_s == 0) break;
+        if (exact && rem_s == 0) break;
         const unsigned need = min(target, max_nms - consumed);
-        const unsigned need_s = hstride == 1 ? need : (need + need / 4 + hstride - 1) / hstride;  // +25% margin
+        const unsigned need_s = hstride == 1 ? need : (need + need / 4 + hstride - 1) / hstride;  // sample: +25% margin
         int lo0 = 0;
         bool single_heavy = false;
         if (rem_s > need_s) {
             const int d = find_digit(S.g0, hi0, base, need_s);
             lo0 = d;
             const unsigned est = (S.g0[d] - base) * hstride;
-            if (est > (hstride == 1 ? cap : cap - cap / 4)) {
+            if (est > (exact ? cap : cap - cap / 4)) {
                 if (S.g0[d + 1] - base > 0) lo0 = d + 1;
-                else single_heavy = (hstride == 1);  // exact: digit d alone exceeds the capacity
+                else single_heavy = exact;  // exact: digit d alone exceeds the capacity
             }
         }
         if (single_heavy) {
@@ -709,6 +814,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
             // estimate was off (or ties piled up): count exactly what is left and retry
             build_hist(1u, (unsigned)hi0);
             hstride = 1;
+            exact = true;
             continue;
         }
         const unsigned take = min(n, max_nms - consumed);

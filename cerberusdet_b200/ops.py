@@ -6,6 +6,8 @@ raises ``TypeError`` -- there is no fallback.
 """
 from __future__ import annotations
 
+import ctypes
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -36,6 +38,8 @@ def _stream_ptr(device) -> int:
 
 @torch.library.custom_op("cerb::decode", mutates_args=())
 def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
+    """Returns ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``; the score summaries ``smax_t`` are empty
+    tensors when the shapes do not allow them (see include/cerb_post.h)."""
     lib = _lib.load()
     T = len(nc)
     if T == 0 or len(levels) % T:
@@ -60,14 +64,20 @@ def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequen
                 raise ValueError(f"task {t} level {l}: expected {(B, 64 + nc[t], H[l], W[l])}, got {tuple(x.shape)}")
             lv.append(x.contiguous())
     ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
+    G = int(lib.cerb_summary_groups(L, _lib.int_array(H), _lib.int_array(W)))
+    sm = [torch.empty((B, nc[t], G), dtype=first.dtype, device=first.device) for t in range(T)]
+    written = ctypes.c_int(0)
     with torch.cuda.device(first.device):
         rc = lib.cerb_decode(
             _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(list(nc)), T, L, B,
             _lib.int_array(H), _lib.int_array(W), _lib.float_array([float(s) for s in strides]), code,
-            _lib.ptr_array([y.data_ptr() for y in ys]), _stream_ptr(first.device),
+            _lib.ptr_array([y.data_ptr() for y in ys]), _lib.ptr_array([x.data_ptr() for x in sm]),
+            ctypes.byref(written), _stream_ptr(first.device),
         )
     _lib.check(rc)
-    return ys
+    if not written.value:
+        sm = [y.new_empty((0,)) for y in ys]
+    return ys + sm
 
 
 @decode_op.register_fake
@@ -76,7 +86,9 @@ def _(levels, nc, strides):
     L = len(levels) // T
     B = levels[0].shape[0]
     A = sum(levels[l].shape[2] * levels[l].shape[3] for l in range(L))
-    return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)]
+    G = sum((levels[l].shape[2] * levels[l].shape[3] + 63) // 64 for l in range(L))
+    return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)] + [
+        levels[0].new_empty((B, nc[t], G)) for t in range(T)]
 
 
 @torch.library.custom_op("cerb::nms", mutates_args=())
@@ -90,6 +102,8 @@ def nms_op(
     max_det: int,
     max_nms: int,
     max_wh: float,
+    smax: Sequence[torch.Tensor],
+    level_hw: Sequence[int],
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     T = len(preds)
@@ -109,11 +123,21 @@ def nms_op(
     ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     cls_arr = _lib.int_array(list(classes)) if classes is not None else None
+    sm_arr, lhw_arr, n_lvl = None, None, 0
+    if len(smax) == T and len(level_hw) > 0:
+        G = sum((h + 63) // 64 for h in level_hw)
+        ok = all(s.is_contiguous() and s.dtype == first.dtype and s.device == dev
+                 and tuple(s.shape) == (B, n, G) for s, n in zip(smax, ncs))
+        ok = ok and all(p.data_ptr() == q.data_ptr() for p, q in zip(preds, ps))  # no hidden copies
+        if ok:
+            sm_arr = _lib.ptr_array([s.data_ptr() for s in smax])
+            lhw_arr, n_lvl = _lib.int_array([int(h) for h in level_hw]), len(level_hw)
     with torch.cuda.device(dev):
         rc = lib.cerb_nms(
             _lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
             float(conf_thres), float(iou_thres), cls_arr, len(classes) if classes is not None else 0,
             int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh),
+            sm_arr, n_lvl, lhw_arr,
             dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
             _stream_ptr(dev),
         )
@@ -122,19 +146,58 @@ def nms_op(
 
 
 @nms_op.register_fake
-def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax, level_hw):
     T, B = len(preds), preds[0].shape[0]
     return (preds[0].new_empty((T, B, max_det, 6), dtype=torch.float32),
             preds[0].new_empty((T, B), dtype=torch.int32))
 
 
+# ----------------------------------------------------------------------------- score-summary registry
+class _Summary:
+    __slots__ = ("ref", "version", "smax", "level_hw")
+
+
+_SUMMARIES: "dict[int, _Summary]" = {}
+
+
+def _remember_summary(y: torch.Tensor, smax: torch.Tensor, level_hw) -> None:
+    """Remember that ``smax`` summarises ``y`` as it is right now.  ``find_summary`` hands it back only for
+    this very tensor (same storage, shape, and no in-place write since), so a stale summary is never used."""
+    if len(_SUMMARIES) > 64:
+        for k in [k for k, v in _SUMMARIES.items() if v.ref() is None]:
+            del _SUMMARIES[k]
+        if len(_SUMMARIES) > 64:
+            _SUMMARIES.clear()
+    ent = _Summary()
+    ent.ref, ent.version, ent.smax, ent.level_hw = weakref.ref(y), y._version, smax, tuple(int(h) for h in level_hw)
+    _SUMMARIES[y.data_ptr()] = ent
+
+
+def find_summary(y: torch.Tensor):
+    ent = _SUMMARIES.get(y.data_ptr())
+    if ent is None:
+        return None
+    t = ent.ref()
+    if t is None or t is not y or y._version != ent.version or not y.is_contiguous():
+        return None
+    return ent.smax, ent.level_hw
+
+
 # ----------------------------------------------------------------------------- friendly wrappers
 def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float]) -> List[torch.Tensor]:
     """``task_levels[t][l]`` = raw head tensor ``[B, 64+nc_t, H_l, W_l]`` -> ``y_t [B, 4+nc_t, A]``
-    for every task in one launch (reference Detect.forward eval branch, models/yolo.py:93-99)."""
+    for every task in one launch (reference Detect.forward eval branch, models/yolo.py:93-99).
+    The kernel also leaves a score summary per task, remembered for ``nms_batched``."""
     flat = [x for lv in task_levels for x in lv]
     nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
-    return decode_op(flat, nc, [float(s) for s in strides])
+    out = decode_op(flat, nc, [float(s) for s in strides])
+    T = len(nc)
+    ys, sms = out[:T], out[T:]
+    level_hw = [int(x.shape[2]) * int(x.shape[3]) for x in task_levels[0]]
+    for y, sm in zip(ys, sms):
+        if sm.numel():
+            _remember_summary(y, sm, level_hw)
+    return ys
 
 
 def nms_batched(
@@ -147,12 +210,20 @@ def nms_batched(
     max_det: int = 300,
     max_nms: int = MAX_NMS,
     max_wh: float = MAX_WH,
+    use_summary: bool = True,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """All task heads, all images, one launch.  Returns padded ``dets[T,B,max_det,6]`` and
-    ``counts[T,B]`` (device tensors; no host sync)."""
+    ``counts[T,B]`` (device tensors; no host sync).  Predictions that came out of ``decode_heads``
+    unmodified bring their score summary along, which spares the kernel the full score scans."""
     # reference asserts (utils/general.py:399-400) -- same exception type and wording
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
-    return nms_op(list(preds), float(conf_thres), float(iou_thres),
+    preds = list(preds)
+    smax, level_hw = [], []
+    if use_summary:
+        found = [find_summary(p) for p in preds]
+        if all(f is not None for f in found) and len({f[1] for f in found}) == 1:
+            smax, level_hw = [f[0] for f in found], list(found[0][1])
+    return nms_op(preds, float(conf_thres), float(iou_thres),
                   None if classes is None else [int(c) for c in classes],
-                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh))
+                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax, level_hw)

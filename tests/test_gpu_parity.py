@@ -156,6 +156,40 @@ def test_nms_wild_boxes_outside_class_window(ops, dtype, multi):
     _assert_rows_equal(got, want, "wild")
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("regime", ["iid", "planted"])
+@pytest.mark.parametrize("kw", [
+    dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300),
+    dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+    dict(conf_thres=0.01, iou_thres=0.5, classes=[0, 5, 11], multi_label=True, max_det=40),
+    dict(conf_thres=0.05, iou_thres=0.5, classes=[2, 3], agnostic=True, max_det=1200),
+])
+def test_decode_then_nms_with_score_summary(ops, dtype, regime, kw):
+    """decode_heads -> nms_batched (summary-guided) == oracle NMS of the same decoded tensor, and
+    == the summary-free kernel path; also after an in-place edit (summary must be dropped)."""
+    from oracle import ref_port as rp
+
+    ncs = [20, 12]
+    heads = synth_heads(range(3), ncs, (320, 256), dtype, regime, cfg=11)
+    ys = ops.decode_heads([[_dev(x) for x in lv] for lv in heads], STRIDES)
+    assert all(ops.find_summary(y) is not None for y in ys)
+    dets, counts = ops.nms_batched(ys, **kw)
+    d0, c0 = ops.nms_batched(ys, use_summary=False, **kw)
+    assert torch.equal(c0, counts) and torch.equal(d0, dets)
+    ch = counts.cpu()
+    for t in range(2):
+        want = rp.nms_port(ys[t].cpu(), greedy="c", **kw)
+        for b in range(3):
+            assert torch.equal(dets[t, b, : ch[t, b]].cpu(), want[b]), (t, b)
+    ys[0][:, 4:] *= 0.5  # in-place edit: the remembered summary no longer describes the tensor
+    assert ops.find_summary(ys[0]) is None
+    dets, counts = ops.nms_batched(ys, **kw)
+    ch = counts.cpu()
+    want = rp.nms_port(ys[0].cpu(), greedy="c", **kw)
+    for b in range(3):
+        assert torch.equal(dets[0, b, : ch[0, b]].cpu(), want[b])
+
+
 def _truncation_prediction(dtype, seed=3):
     """> 30000 multi-label candidates, nearly all inside one heavy cluster (suppressed by its top box)
     plus isolated boxes whose scores straddle the rank-30000 cut: the kept set is sensitive to the exact
@@ -240,6 +274,9 @@ def test_full_size_properties_cfg3(ops):
     ys = ops.decode_heads(dev_heads, STRIDES)
     kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
     dets, counts = ops.nms_batched(ys, **kw)
+    # the score summary left by the decode kernel only steers which groups are read: same bits without it
+    d0, c0 = ops.nms_batched(ys, use_summary=False, **kw)
+    assert torch.equal(c0, counts) and torch.equal(d0, dets)
     counts_h = counts.cpu()
     assert (counts_h <= 300).all() and (counts_h > 0).all()
     for t in range(3):
