@@ -18,7 +18,7 @@ EXPORTS = (
     "cerb_version",
     "cerb_last_error",
     "cerb_decode",
-    "cerb_summary_groups",
+    "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
     "cerb_debug_set_chunking",
@@ -51,12 +51,12 @@ def load() -> ctypes.CDLL:
     lib.cerb_last_error.argtypes = []
     lib.cerb_decode.restype = i
     lib.cerb_decode.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
-    lib.cerb_summary_groups.restype = sz
-    lib.cerb_summary_groups.argtypes = [i, ip, ip]
+    lib.cerb_summary_row_len.restype = sz
+    lib.cerb_summary_row_len.argtypes = [i, i]
     lib.cerb_nms_workspace_bytes.restype = sz
     lib.cerb_nms_workspace_bytes.argtypes = [i, i, i]
     lib.cerb_nms.restype = i
-    lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, i, ip, vp, vp, vp, sz, vp]
+    lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp]
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
     lib.cerb_debug_set_hist_sample.restype = i

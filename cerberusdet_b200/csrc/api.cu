@@ -45,11 +45,10 @@ extern "C" int cerb_debug_set_hist_sample(int stride) {
     return 0;
 }
 
-extern "C" size_t cerb_summary_groups(int L, const int* H, const int* W) {
-    size_t g = 0;
-    if (!H || !W) return 0;
-    for (int l = 0; l < L; ++l) g += ((size_t)H[l] * W[l] + CERB_SUM_GROUP - 1) / CERB_SUM_GROUP;
-    return g;
+extern "C" size_t cerb_summary_row_len(int A, int dtype) {
+    const size_t V = dtype == CERB_F16 ? 8 : 4;
+    if (A <= 0 || (size_t)A % V) return 0;
+    return ((size_t)A / V + V - 1) / V * V;
 }
 
 extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
@@ -66,21 +65,18 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
     P.T = T; P.L = L; P.B = B; P.nrows = T * L;
     const size_t elt = dtype == CERB_F16 ? 2 : 4;
     int vec = (int)(16 / elt);
-    long A = 0, G = 0;
+    long A = 0;
     if (summary_written) *summary_written = 0;
     for (int l = 0; l < L; ++l) {
         REQUIRE(H[l] > 0 && W[l] > 0, "cerb_decode: level %d has empty shape %dx%d", l, H[l], W[l]);
         const long hw = (long)H[l] * W[l];
         REQUIRE(hw < (1l << 30), "cerb_decode: level %d too large", l);
         P.hw[l] = (int)hw; P.w[l] = W[l]; P.aoff[l] = (int)A; P.stride[l] = strides[l];
-        P.goff[l] = (int)G;
         A += hw;
-        G += (hw + CERB_SUM_GROUP - 1) / CERB_SUM_GROUP;
         while (vec > 1 && hw % vec) vec >>= 1;
     }
     REQUIRE(A < (1l << 30), "cerb_decode: too many anchors");
     P.A = (int)A;
-    P.G = (int)G;
     for (int t = 0; t < T; ++t) {
         REQUIRE(nc[t] >= 1, "cerb_decode: task %d has nc=%d", t, nc[t]);
         P.nc[t] = nc[t];
@@ -95,10 +91,10 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
         }
     }
     if (B == 0) return 0;
-    // the score summary needs the full 128-bit path (its groups are whole, aligned lane groups)
+    // the score summary (one maximum per 16-byte score vector) needs the full 128-bit path
     if (smax != nullptr && vec == (int)(16 / elt)) {
         bool all = true;
-        for (int t = 0; t < T; ++t) all = all && smax[t] != nullptr;
+        for (int t = 0; t < T; ++t) all = all && smax[t] != nullptr && aligned_to(smax[t], 16);
         if (all) {
             for (int t = 0; t < T; ++t) P.smax[t] = smax[t];
             if (summary_written) *summary_written = 1;
@@ -134,8 +130,7 @@ static float iou_threshold_as_float(double thr) {
 
 extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                         double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
-                        int max_det, int max_nms, double max_wh, const void* const* smax, int L, const int* level_hw,
-                        float* dets, int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+                        int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes, void* stream) {
     g_err[0] = 0;
     REQUIRE(pred && nc, "cerb_nms: null argument");
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_nms: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
@@ -168,19 +163,10 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
             REQUIRE(nc[t] <= 32 * CERB_MAX_CLASS_WORDS, "cerb_nms: class filter supports nc <= %d", 32 * CERB_MAX_CLASS_WORDS);
     }
     if (smax != nullptr) {
-        REQUIRE(level_hw != nullptr && L >= 1 && L <= CERB_MAX_LEVELS, "cerb_nms: a score summary needs the level sizes");
         const int V = dtype == CERB_F16 ? 8 : 4;
-        long a = 0, g = 0;
-        for (int l = 0; l < L; ++l) {
-            REQUIRE(level_hw[l] > 0 && level_hw[l] % V == 0, "cerb_nms: summary level %d size %d not a multiple of %d", l, level_hw[l], V);
-            P.lvl_hw[l] = level_hw[l]; P.lvl_aoff[l] = (int)a; P.lvl_goff[l] = (int)g;
-            a += level_hw[l];
-            g += (level_hw[l] + CERB_SUM_GROUP - 1) / CERB_SUM_GROUP;
-        }
-        REQUIRE(a == A, "cerb_nms: summary levels cover %ld anchors, prediction has %d", a, A);
-        P.G = (int)g; P.L = L;
+        REQUIRE(A % V == 0, "cerb_nms: a score summary needs A (%d) to be a multiple of %d", A, V);
         for (int t = 0; t < T; ++t) {
-            REQUIRE(smax[t] != nullptr, "cerb_nms: smax[%d] is null", t);
+            REQUIRE(smax[t] != nullptr && aligned_to(smax[t], 16), "cerb_nms: smax[%d] is null or misaligned", t);
             REQUIRE(aligned_to(pred[t], 16), "cerb_nms: summary path needs 16-byte aligned predictions");
             P.smax[t] = smax[t];
         }

@@ -2,7 +2,6 @@
 #pragma once
 #include "cerb_common.cuh"
 
-#define CERB_SUM_GROUP 64  // anchors per score-summary group (never straddles a level)
 
 // ------------------------------------------------------------------ decode
 struct DecodeParams {
@@ -17,10 +16,7 @@ struct DecodeParams {
     int nrows;                                                  // T * L
     int row_start[CERB_MAX_TASKS * CERB_MAX_LEVELS + 1];        // first block of each (task, level) row
     int row_blocks_per_part[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // ceil(B * nvecp / threads)
-    int row_nvecp[CERB_MAX_TASKS * CERB_MAX_LEVELS];            // vectors per image, padded to whole summary groups
-    void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, G]: max score per (class, 64-anchor group)
-    int goff[CERB_MAX_LEVELS];   // first summary group of each level
-    int G;                       // summary groups per class: sum_l ceil(hw_l / 64)
+    void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V]: max of every 16-byte score vector
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
 
@@ -45,9 +41,7 @@ struct NmsParams {
     int chunk_first; // size target of the first chunk
     int hist_sample; // stride (in 16-byte vectors) of the estimating histogram; 1 = exact
     int class_shortcut; // 1 if different-class tame boxes provably never intersect after the offset
-    const void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, G] from the decode kernel (else null)
-    int G, L;                          // summary groups per class; levels
-    int lvl_hw[CERB_MAX_LEVELS], lvl_aoff[CERB_MAX_LEVELS], lvl_goff[CERB_MAX_LEVELS];
+    const void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V] from the decode kernel (else null)
     float tame_lo, tame_hi; // the window of "tame" un-offset coordinates, tame_hi - tame_lo == class_gap
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);

@@ -46,6 +46,19 @@ template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, 
     }
 }
 
+// maximum of the VEC stored (already rounded) scores of one vector; scores are sigmoids, so no NaN unless the
+// logit was NaN, which fmaxf / __hmax2 drop -- a NaN score is never a candidate either
+template <typename T, int VEC> __device__ __forceinline__ T pack_max(const Pack<T, VEC>& v);
+template <> __device__ __forceinline__ __half pack_max<__half, 8>(const Pack<__half, 8>& v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v.raw);
+    const __half2 m = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
+    return __hmax(__low2half(m), __high2half(m));
+}
+template <> __device__ __forceinline__ float pack_max<float, 4>(const Pack<float, 4>& v) {
+    return fmaxf(fmaxf(v.e[0], v.e[1]), fmaxf(v.e[2], v.e[3]));
+}
+template <typename T, int VEC> __device__ __forceinline__ T pack_max(const Pack<T, VEC>& v) { return v.e[0]; }
+
 // Expected DFL distance of one box side for VEC anchors: sum_k k * softmax(logits)_k.
 // Rounding points follow the reference for half tensors: probabilities are rounded to
 // half (softmax output), the 1x1 conv accumulates in fp32 and rounds once.
@@ -98,15 +111,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_consta
 
     const int hw = P.hw[level];
     const int nvec = hw / VEC;
-    // Vectors per image are padded to a whole number of 64-anchor score-summary groups so that the lanes of
-    // one group are always LPG consecutive, aligned lanes (see the summary below).
-    constexpr int LPG = (CERB_SUM_GROUP / VEC) <= 32 ? (CERB_SUM_GROUP / VEC) : 32;
-    const int nvecp = P.row_nvecp[row];
     const int item = vblk * DEC_THREADS + threadIdx.x;
-    const int b = item / nvecp;
-    const int v = item - b * nvecp;
-    const bool valid = (b < P.B) && (v < nvec);
-    if (part < 2 && !valid) return;
+    if (item >= P.B * nvec) return;
+    const int b = item / nvec;
+    const int v = item - b * nvec;
     const int a0 = v * VEC;  // first anchor inside the level
 
     const int nc = P.nc[task];
@@ -137,60 +145,42 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_consta
         store_pack<T, VEC>(out + (size_t)part * P.A, oc);
         store_pack<T, VEC>(out + (size_t)(part + 2) * P.A, os);
     } else {
-        // class scores: sigmoid (yolo.py:99).  Optionally also the score summary: the maximum score of each
-        // (class, 64-anchor group), which lets the NMS kernel skip the groups that cannot hold a candidate.
+        // class scores: sigmoid (yolo.py:99).  Optionally also the score summary: the maximum of each
+        // 16-byte vector of scores (one value per class and VEC consecutive anchors), which lets the NMS
+        // kernel read only the vectors that can hold a candidate.
         const int c0 = (part - 2) * CLS_CHUNK;
         const int c1 = min(nc, c0 + CLS_CHUNK);
         const T* __restrict__ cin = in + (size_t)(4 * CERB_REG_MAX) * hw;
         T* __restrict__ cout = out + (size_t)4 * P.A;
-        T* __restrict__ smax = nullptr;
-        if (CERB_SUM_GROUP % VEC == 0 && CERB_SUM_GROUP / VEC <= 32 && P.smax[task] != nullptr && b < P.B)
-            smax = reinterpret_cast<T*>(P.smax[task]) + (size_t)b * nc * P.G + P.goff[level] + v / LPG;
-        const bool writer = (threadIdx.x % LPG) == 0;
+        T* __restrict__ smax = nullptr;  // [B, nc, srow], srow = roundup(A / VEC, VEC)
+        const size_t srow = ((size_t)(P.A / VEC) + VEC - 1) / VEC * VEC;
+        if (sizeof(T) * VEC == 16 && P.smax[task] != nullptr)
+            smax = reinterpret_cast<T*>(P.smax[task]) + (size_t)b * nc * srow + (P.aoff[level] + a0) / VEC;
         int c = c0;
         for (; c + 4 <= c1; c += 4) {
             Pack<T, VEC> vv[4];
-            if (valid) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) vv[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
-            }
+            for (int u = 0; u < 4; ++u) vv[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float mx = -INFINITY;
-                if (valid) {
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float x = to_f32<T>(vv[u].e[i]);
-                        vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
-                        mx = fmaxf(mx, to_f32<T>(vv[u].e[i]));
-                    }
-                    store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, vv[u]);
+                for (int i = 0; i < VEC; ++i) {
+                    const float x = to_f32<T>(vv[u].e[i]);
+                    vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
                 }
-                if (P.smax[task] != nullptr) {  // block-uniform
-#pragma unroll
-                    for (int o = 1; o < LPG; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    if (smax != nullptr && writer && v < nvec) smax[(size_t)(c + u) * P.G] = from_f32<T>(mx);
-                }
+                store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, vv[u]);
+                if (smax != nullptr) smax[(size_t)(c + u) * srow] = pack_max<T, VEC>(vv[u]);
             }
         }
         for (; c < c1; ++c) {
-            Pack<T, VEC> v1;
-            float mx = -INFINITY;
-            if (valid) {
-                v1 = load_pack<T, VEC>(cin + (size_t)c * hw);
+            Pack<T, VEC> v1 = load_pack<T, VEC>(cin + (size_t)c * hw);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float x = to_f32<T>(v1.e[i]);
-                    v1.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
-                    mx = fmaxf(mx, to_f32<T>(v1.e[i]));
-                }
-                store_pack<T, VEC>(cout + (size_t)c * P.A, v1);
+            for (int i = 0; i < VEC; ++i) {
+                const float x = to_f32<T>(v1.e[i]);
+                v1.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
             }
-            if (P.smax[task] != nullptr) {
-#pragma unroll
-                for (int o = 1; o < LPG; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                if (smax != nullptr && writer && v < nvec) smax[(size_t)c * P.G] = from_f32<T>(mx);
-            }
+            store_pack<T, VEC>(cout + (size_t)c * P.A, v1);
+            if (smax != nullptr) smax[(size_t)c * srow] = pack_max<T, VEC>(v1);
         }
     }
 }
@@ -200,11 +190,7 @@ template <typename T, int VEC> static cudaError_t launch_decode_t(DecodeParams& 
     for (int t = 0; t < P.T; ++t)
         for (int l = 0; l < P.L; ++l) {
             const int row = t * P.L + l;
-            constexpr int LPG = (CERB_SUM_GROUP / VEC) <= 32 ? (CERB_SUM_GROUP / VEC) : 32;
-            const int nvec = P.hw[l] / VEC;
-            const int nvecp = (nvec + LPG - 1) / LPG * LPG;
-            P.row_nvecp[row] = nvecp;
-            const long items = (long)P.B * nvecp;
+            const long items = (long)P.B * (P.hw[l] / VEC);
             const int bpp = (int)((items + DEC_THREADS - 1) / DEC_THREADS);
             const int parts = 2 + (P.nc[t] + CLS_CHUNK - 1) / CLS_CHUNK;
             P.row_start[row] = blocks;

@@ -103,12 +103,40 @@ __device__ __forceinline__ u64 make_key(unsigned sbits, unsigned idx) {
     return ((u64)sbits << 32) | (u64)(0xFFFFFFFFu - idx);
 }
 
+// Warp-aggregated shared-memory atomics: many lanes of a warp hitting ONE address serialise otherwise.
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// all currently active lanes take consecutive slots of *counter; returns this lane's slot
+__device__ __forceinline__ unsigned warp_take_slot(unsigned* counter) {
+    const unsigned active = __activemask();
+    const int leader = __ffs(active) - 1;
+    unsigned base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, (unsigned)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & lanemask_lt());
+}
+// every active lane adds 1 to hist[bin]; lanes with equal bins are merged into one atomic
+__device__ __forceinline__ void warp_hist_add(unsigned* hist, unsigned bin) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, bin);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
 template <typename T> struct ScoreVec {
     static constexpr int V = 16 / sizeof(T);
     union { uint4 raw; T e[16 / sizeof(T)]; };
 };
 
 #define SCAN_UNROLL 4
+
+// padded length of one class row of the score summary: roundup(A / V, V) entries (rows stay 16-byte aligned)
+template <typename T> __host__ __device__ __forceinline__ size_t summary_row_len(int A) {
+    const size_t V = 16 / sizeof(T);
+    return ((size_t)A / V + V - 1) / V * V;
+}
 
 // Per-dtype form of the score-bit range [sb_lo, sb_hi] (positive floats: bit order == value order).
 template <typename T> struct RangeBounds;
@@ -267,93 +295,155 @@ __device__ __forceinline__ void for_each_candidate(const T* __restrict__ img, in
     }
 }
 
-// ---- the same enumeration guided by the score summary (max score of every (class, 64-anchor group),
-// written by the decode kernel): only the groups whose maximum reaches sb_lo are read at all.  `hits` is a
-// shared-memory scratch list of NMS_BINS entries.  with_scores == false only visits the summary itself and
-// reports one pseudo-candidate per group (its maximum) -- that is the estimating histogram.
+// ---- the same enumeration guided by the score summary written by the decode kernel: smax[c][vi] is the
+// maximum of score vector vi (V consecutive anchors) of class c, rows padded to SNV = roundup(A/V, V) entries.
+// Pass 1 reads the summary and lists the score vectors whose maximum reaches sb_lo (shared-memory list `hits`,
+// NMS_BINS entries); pass 2 reads just those.  Returns false -- having reported nothing -- when the list
+// overflows: then the candidates are dense and the caller runs the plain scan instead.
+// WITH_SCORES == false stops after pass 1 and reports one pseudo-candidate per listed vector (its maximum):
+// that is the estimating histogram.
 template <typename T, bool MULTI, bool WITH_SCORES, typename F>
-__device__ __forceinline__ void for_each_candidate_summary(const T* __restrict__ img, const T* __restrict__ smax,
+__device__ __forceinline__ bool for_each_candidate_summary(const T* __restrict__ img, const T* __restrict__ smax,
                                                            int nc, int A, float thr, const NmsParams& P, F f,
                                                            unsigned sb_lo, unsigned sb_hi, unsigned* hits,
                                                            unsigned* nhits) {
     constexpr int V = ScoreVec<T>::V;
-    constexpr int VPG = CERB_SUM_GROUP / V;  // vectors per group
     const T* __restrict__ sc = img + (size_t)4 * A;
-    const unsigned G = (unsigned)P.G;
+    const unsigned NV = (unsigned)A / V;          // score vectors per class row
+    const unsigned SNV = (NV + V - 1) / V * V;    // padded summary row length
+    const unsigned SV = SNV / V;                  // 16-byte summary vectors per row
     const bool filt = P.use_class_filter != 0;
     {
         const unsigned tb = __float_as_uint(thr) + 1u;
         sb_lo = sb_lo > tb ? sb_lo : tb;
         sb_hi = sb_hi < 0x7F800000u ? sb_hi : 0x7F800000u;
     }
-    if (sb_lo > sb_hi) return;
+    if (sb_lo > sb_hi) return true;
     const RangeBounds<T> rb = make_range_bounds<T>(sb_lo, sb_hi);
-    const unsigned entries = MULTI ? (unsigned)nc * G : G;
-    for (unsigned slab = 0; slab < entries; slab += NMS_BINS) {
+    const RangeBounds<T> rb_any = make_range_bounds<T>(sb_lo, 0x7F800000u);  // "maximum reaches sb_lo"
+    const unsigned nsv = MULTI ? (unsigned)nc * SV : SV;
+    if (WITH_SCORES) {
         __syncthreads();
         if (threadIdx.x == 0) *nhits = 0;
         __syncthreads();
-        const unsigned slab_end = min(entries, slab + (unsigned)NMS_BINS);
-        for (unsigned e = slab + threadIdx.x; e < slab_end; e += NMS_THREADS) {
-            unsigned sbm;
-            if (MULTI) {
-                if (filt) { const unsigned c = e / G; if (!((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue; }
-                sbm = make_sbits(to_f32<T>(__ldg(smax + e)));
-            } else {
-                float mx = to_f32<T>(__ldg(smax + e));
-                for (int c = 1; c < nc; ++c) mx = fmaxf(mx, to_f32<T>(__ldg(smax + (size_t)c * G + e)));
-                sbm = make_sbits(mx);
-            }
-            if (sbm >= sb_lo && sbm <= 0x7F800000u) {
-                if (WITH_SCORES) hits[atomicAdd(nhits, 1u)] = e;
-                else if (sbm <= sb_hi) f(sbm, 0, 0);
+    }
+    // ---- pass 1: the summary
+    for (unsigned q0 = threadIdx.x; q0 < nsv; q0 += NMS_THREADS * SCAN_UNROLL) {
+        ScoreVec<T> m[SCAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; ++u) {
+            const unsigned q = q0 + u * NMS_THREADS;
+            if (q < nsv) {
+                const unsigned c = MULTI ? q / SV : 0u;
+                const unsigned j0 = (MULTI ? q - c * SV : q) * V;
+                m[u].raw = __ldg(reinterpret_cast<const uint4*>(smax + (size_t)c * SNV + j0));
             }
         }
-        if (!WITH_SCORES) continue;
-        __syncthreads();
-        const unsigned items = *nhits * VPG;
-        for (unsigned it = threadIdx.x; it < items; it += NMS_THREADS) {
-            const unsigned e = hits[it / VPG], j = it % VPG;
-            const unsigned c = MULTI ? e / G : 0u, g = MULTI ? e - c * G : e;
-            int l = 0;
-            while (l + 1 < P.L && g >= (unsigned)P.lvl_goff[l + 1]) ++l;
-            const unsigned a_in = (g - (unsigned)P.lvl_goff[l]) * CERB_SUM_GROUP + j * V;
-            if (a_in >= (unsigned)P.lvl_hw[l]) continue;
-            const unsigned a_s = (unsigned)P.lvl_aoff[l] + a_in;
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; ++u) {
+            const unsigned q = q0 + u * NMS_THREADS;
+            if (q >= nsv) break;
+            const unsigned c = MULTI ? q / SV : 0u;
+            const unsigned j0 = (MULTI ? q - c * SV : q) * V;  // first entry of this summary vector in its row
             if (MULTI) {
-                ScoreVec<T> v;
-                v.raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)c * A + a_s));
-                const unsigned h = range_hits<T>(v, sb_lo, sb_hi, rb);
-                if (!h) continue;
-#pragma unroll
-                for (int k = 0; k < V; ++k)
-                    if ((h >> k) & 1u) f(make_sbits(to_f32<T>(v.e[k])), (int)(a_s + k), (int)c);
+                if (filt && !((P.class_mask[c >> 5] >> (c & 31)) & 1u)) continue;
             } else {
-                float best[V];
-                int bc[V];
+                for (int cc = 1; cc < nc; ++cc) {
+                    ScoreVec<T> o;
+                    o.raw = __ldg(reinterpret_cast<const uint4*>(smax + (size_t)cc * SNV + j0));
 #pragma unroll
-                for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bc[k] = 0; }
-                for (int cc = 0; cc < nc; ++cc) {
-                    ScoreVec<T> v;
-                    v.raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)cc * A + a_s));
-#pragma unroll
-                    for (int k = 0; k < V; ++k) {
-                        const float sv = to_f32<T>(v.e[k]);
-                        if (cc == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc; }  // lowest index wins ties
-                    }
+                    for (int k = 0; k < V; ++k)
+                        if (to_f32<T>(o.e[k]) > to_f32<T>(m[u].e[k])) m[u].e[k] = o.e[k];
                 }
+            }
+            const unsigned h = range_hits<T>(m[u], sb_lo, 0x7F800000u, rb_any);
+            if (!h) continue;
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const unsigned sb = make_sbits(best[k]);
-                    if (sb - sb_lo <= sb_hi - sb_lo) {
-                        if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
-                        f(sb, (int)(a_s + k), bc[k]);
-                    }
+            for (int k = 0; k < V; ++k) {
+                if (!((h >> k) & 1u) || j0 + k >= NV) continue;
+                if (WITH_SCORES) {
+                    const unsigned p = atomicAdd(nhits, 1u);
+                    if (p < NMS_BINS) hits[p] = c * NV + j0 + k;
+                } else {
+                    const unsigned sbm = make_sbits(to_f32<T>(m[u].e[k]));
+                    if (sbm <= sb_hi) f(sbm, 0, 0);
                 }
             }
         }
     }
+    if (!WITH_SCORES) return true;
     __syncthreads();
+    const unsigned nh = *nhits;
+    __syncthreads();
+    if (nh > NMS_BINS) return false;  // dense: not worth (and not possible) to list
+    // ---- pass 2: the listed score vectors
+    if (MULTI) {
+        for (unsigned i0 = threadIdx.x; i0 < nh; i0 += NMS_THREADS * SCAN_UNROLL) {
+            ScoreVec<T> v[SCAN_UNROLL];
+            unsigned e_[SCAN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u) {
+                const unsigned i = i0 + u * NMS_THREADS;
+                if (i < nh) {
+                    e_[u] = hits[i];
+                    const unsigned c = e_[u] / NV;
+                    v[u].raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)c * A + (size_t)(e_[u] - c * NV) * V));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u) {
+                const unsigned i = i0 + u * NMS_THREADS;
+                if (i >= nh) break;
+                const unsigned hv = range_hits<T>(v[u], sb_lo, sb_hi, rb);
+                if (!hv) continue;
+                const unsigned c = e_[u] / NV, a_s = (e_[u] - c * NV) * V;
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if ((hv >> k) & 1u) f(make_sbits(to_f32<T>(v[u].e[k])), (int)(a_s + k), (int)c);
+            }
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < nh; i += NMS_THREADS) {
+            const unsigned a_s = hits[i] * V;
+            const uint4* __restrict__ col = reinterpret_cast<const uint4*>(sc + a_s);
+            const size_t rowv = (size_t)A / V;
+            float best[V];
+            int bc[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bc[k] = 0; }
+            int cc = 0;
+            for (; cc + SCAN_UNROLL <= nc; cc += SCAN_UNROLL) {
+                ScoreVec<T> v[SCAN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u) v[u].raw = __ldg(col + (size_t)(cc + u) * rowv);
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u)
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float sv = to_f32<T>(v[u].e[k]);
+                        if ((cc + u) == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc + u; }  // lowest index wins ties
+                    }
+            }
+            for (; cc < nc; ++cc) {
+                ScoreVec<T> v1;
+                v1.raw = __ldg(col + (size_t)cc * rowv);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float sv = to_f32<T>(v1.e[k]);
+                    if (cc == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const unsigned sb = make_sbits(best[k]);
+                if (sb - sb_lo <= sb_hi - sb_lo) {
+                    if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
+                    f(sb, (int)(a_s + k), bc[k]);
+                }
+            }
+        }
+    }
+    return true;
 }
 
 __device__ __forceinline__ int level_shift(int lvl) { return lvl < 5 ? 52 - 12 * lvl : 0; }
@@ -454,8 +544,11 @@ template <int E> __device__ __forceinline__ void block_sort_desc(u64* keys) {
     __syncthreads();
 }
 
+#ifndef NMS_MINB
+#define NMS_MINB 2
+#endif
 template <typename T, bool MULTI>
-__global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_constant__ NmsParams P) {
+__global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
@@ -494,13 +587,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
     PROF_DECL
     const unsigned max_nms = (unsigned)max(P.max_nms, 0);
     const T* __restrict__ smax =
-        P.smax[task] ? reinterpret_cast<const T*>(P.smax[task]) + (size_t)b * nc * P.G : nullptr;
+        P.smax[task] ? reinterpret_cast<const T*>(P.smax[task]) + (size_t)b * nc * summary_row_len<T>(A) : nullptr;
     unsigned hstride = 1;  // > 1: the histogram is a 1/hstride sample
     if (!smax && MULTI && P.hist_sample > 1) {
         const u64 nvec = ((u64)nc * (u64)A) / ScoreVec<T>::V;
         if (nvec >= 8192 && (A % ScoreVec<T>::V) == 0) hstride = (unsigned)P.hist_sample;
     }
     bool exact = (hstride == 1) && !smax;  // histogram counts every candidate
+    bool summary_dense = false;
     auto build_hist = [&](unsigned stride, unsigned below_digit) {
         for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
         __syncthreads();
@@ -510,8 +604,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
         __syncthreads();
         suffix_scan(S.g0, S.warp_tot);
     };
-    // with a score summary the histogram counts GROUPS by their maximum: a lower bound on the candidates of
-    // every digit range (each group contributes at least its maximum), which is all the chunk search needs
+    // with a score summary the histogram counts score VECTORS by their maximum: a lower bound on the candidates
+    // of every digit range (each vector contributes at least its maximum), which is all the chunk search needs
     auto build_hist_summary = [&]() {
         for (int i = tid; i < NMS_BINS; i += NMS_THREADS) S.g0[i] = 0;
         __syncthreads();
@@ -726,8 +820,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_kernel(const __grid_consta
                 if (p < NMS_CAP) S.keys[p] = key;
             }
         };
-        if (smax) for_each_candidate_summary<T, MULTI, true>(img, smax, nc, A, thr, P, put, sb_lo, sb_hi, S.g1, &S.nhits);
-        else for_each_candidate<T, MULTI>(img, nc, A, thr, P, put, sb_lo, sb_hi);
+        bool done = false;
+        if (smax && !summary_dense)
+            done = for_each_candidate_summary<T, MULTI, true>(img, smax, nc, A, thr, P, put, sb_lo, sb_hi, S.g1, &S.nhits);
+        if (!done) {
+            summary_dense = true;  // candidates are dense in this segment: the plain scan is the better tool
+            for_each_candidate<T, MULTI>(img, nc, A, thr, P, put, sb_lo, sb_hi);
+        }
         __syncthreads();
         const unsigned n = S.counter;
         __syncthreads();

@@ -64,8 +64,8 @@ def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequen
                 raise ValueError(f"task {t} level {l}: expected {(B, 64 + nc[t], H[l], W[l])}, got {tuple(x.shape)}")
             lv.append(x.contiguous())
     ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
-    G = int(lib.cerb_summary_groups(L, _lib.int_array(H), _lib.int_array(W)))
-    sm = [torch.empty((B, nc[t], G), dtype=first.dtype, device=first.device) for t in range(T)]
+    R = int(lib.cerb_summary_row_len(A, code))
+    sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
     written = ctypes.c_int(0)
     with torch.cuda.device(first.device):
         rc = lib.cerb_decode(
@@ -86,9 +86,10 @@ def _(levels, nc, strides):
     L = len(levels) // T
     B = levels[0].shape[0]
     A = sum(levels[l].shape[2] * levels[l].shape[3] for l in range(L))
-    G = sum((levels[l].shape[2] * levels[l].shape[3] + 63) // 64 for l in range(L))
+    V = 16 // levels[0].element_size()
+    R = (A // V + V - 1) // V * V
     return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)] + [
-        levels[0].new_empty((B, nc[t], G)) for t in range(T)]
+        levels[0].new_empty((B, nc[t], R)) for t in range(T)]
 
 
 @torch.library.custom_op("cerb::nms", mutates_args=())
@@ -103,7 +104,6 @@ def nms_op(
     max_nms: int,
     max_wh: float,
     smax: Sequence[torch.Tensor],
-    level_hw: Sequence[int],
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     T = len(preds)
@@ -123,21 +123,20 @@ def nms_op(
     ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     cls_arr = _lib.int_array(list(classes)) if classes is not None else None
-    sm_arr, lhw_arr, n_lvl = None, None, 0
-    if len(smax) == T and len(level_hw) > 0:
-        G = sum((h + 63) // 64 for h in level_hw)
-        ok = all(s.is_contiguous() and s.dtype == first.dtype and s.device == dev
-                 and tuple(s.shape) == (B, n, G) for s, n in zip(smax, ncs))
+    sm_arr = None
+    if len(smax) == T:
+        R = int(lib.cerb_summary_row_len(A, code))
+        ok = R > 0 and all(s.is_contiguous() and s.dtype == first.dtype and s.device == dev
+                           and tuple(s.shape) == (B, n, R) for s, n in zip(smax, ncs))
         ok = ok and all(p.data_ptr() == q.data_ptr() for p, q in zip(preds, ps))  # no hidden copies
         if ok:
             sm_arr = _lib.ptr_array([s.data_ptr() for s in smax])
-            lhw_arr, n_lvl = _lib.int_array([int(h) for h in level_hw]), len(level_hw)
     with torch.cuda.device(dev):
         rc = lib.cerb_nms(
             _lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
             float(conf_thres), float(iou_thres), cls_arr, len(classes) if classes is not None else 0,
             int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh),
-            sm_arr, n_lvl, lhw_arr,
+            sm_arr,
             dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
             _stream_ptr(dev),
         )
@@ -146,7 +145,7 @@ def nms_op(
 
 
 @nms_op.register_fake
-def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax, level_hw):
+def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax):
     T, B = len(preds), preds[0].shape[0]
     return (preds[0].new_empty((T, B, max_det, 6), dtype=torch.float32),
             preds[0].new_empty((T, B), dtype=torch.int32))
@@ -154,13 +153,13 @@ def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max
 
 # ----------------------------------------------------------------------------- score-summary registry
 class _Summary:
-    __slots__ = ("ref", "version", "smax", "level_hw")
+    __slots__ = ("ref", "version", "smax")
 
 
 _SUMMARIES: "dict[int, _Summary]" = {}
 
 
-def _remember_summary(y: torch.Tensor, smax: torch.Tensor, level_hw) -> None:
+def _remember_summary(y: torch.Tensor, smax: torch.Tensor) -> None:
     """Remember that ``smax`` summarises ``y`` as it is right now.  ``find_summary`` hands it back only for
     this very tensor (same storage, shape, and no in-place write since), so a stale summary is never used."""
     if len(_SUMMARIES) > 64:
@@ -169,7 +168,7 @@ def _remember_summary(y: torch.Tensor, smax: torch.Tensor, level_hw) -> None:
         if len(_SUMMARIES) > 64:
             _SUMMARIES.clear()
     ent = _Summary()
-    ent.ref, ent.version, ent.smax, ent.level_hw = weakref.ref(y), y._version, smax, tuple(int(h) for h in level_hw)
+    ent.ref, ent.version, ent.smax = weakref.ref(y), y._version, smax
     _SUMMARIES[y.data_ptr()] = ent
 
 
@@ -180,7 +179,7 @@ def find_summary(y: torch.Tensor):
     t = ent.ref()
     if t is None or t is not y or y._version != ent.version or not y.is_contiguous():
         return None
-    return ent.smax, ent.level_hw
+    return ent.smax
 
 
 # ----------------------------------------------------------------------------- friendly wrappers
@@ -193,10 +192,9 @@ def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequenc
     out = decode_op(flat, nc, [float(s) for s in strides])
     T = len(nc)
     ys, sms = out[:T], out[T:]
-    level_hw = [int(x.shape[2]) * int(x.shape[3]) for x in task_levels[0]]
     for y, sm in zip(ys, sms):
         if sm.numel():
-            _remember_summary(y, sm, level_hw)
+            _remember_summary(y, sm)
     return ys
 
 
@@ -219,11 +217,11 @@ def nms_batched(
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     preds = list(preds)
-    smax, level_hw = [], []
+    smax = []
     if use_summary:
         found = [find_summary(p) for p in preds]
-        if all(f is not None for f in found) and len({f[1] for f in found}) == 1:
-            smax, level_hw = [f[0] for f in found], list(found[0][1])
+        if all(f is not None for f in found):
+            smax = found
     return nms_op(preds, float(conf_thres), float(iou_thres),
                   None if classes is None else [int(c) for c in classes],
-                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax, level_hw)
+                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)

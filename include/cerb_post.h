@@ -61,14 +61,15 @@ int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, cons
 
 /*
  * Score summary (optional by-product of cerb_decode, optional input of cerb_nms).
- *   smax[t]   [B, nc[t], G] in the tensor dtype, G = cerb_summary_groups(L, H, W): the maximum
- *             score of every (class, group of 64 consecutive anchors of one level).
+ *   smax[t]   [B, nc[t], R] in the tensor dtype, R = cerb_summary_row_len(A, dtype): entry (b, c, i) is
+ *             the maximum of the 16-byte score vector i of class c, i.e. of the scores of anchors
+ *             [i*V, i*V+V), V = 8 (fp16) / 4 (fp32); rows are padded to a multiple of V entries.
  * cerb_decode fills it when `smax` is non-NULL and the tensors allow the 128-bit path (every
- * H[l]*W[l] a multiple of 8 (fp16) / 4 (fp32), 16-byte aligned pointers) and then sets
- * *summary_written = 1.  cerb_nms uses it only to skip groups that cannot hold a candidate;
- * results are identical with and without it.  It must describe exactly the `pred` passed.
+ * H[l]*W[l] a multiple of V, 16-byte aligned pointers) and then sets *summary_written = 1.
+ * cerb_nms uses it only to skip score vectors that cannot hold a candidate; results are identical
+ * with and without it.  It must describe exactly the `pred` passed.
  */
-size_t cerb_summary_groups(int L, const int* H, const int* W);
+size_t cerb_summary_row_len(int A, int dtype);
 
 /* Bytes of device workspace cerb_nms / cerb_decode_nms need (0 unless max_det is large). */
 size_t cerb_nms_workspace_bytes(int T, int B, int max_det);
@@ -87,8 +88,7 @@ size_t cerb_nms_workspace_bytes(int T, int B, int max_det);
  *               (conf to the tensor dtype; IoU quotient compared in double)
  *   classes     optional host list of class ids to keep (NULL / 0 = all)
  *   max_nms     30000 in the reference (:416); max_wh 7680 (:415)
- *   smax, L, level_hw   optional score summary from cerb_decode for exactly these predictions
- *               (level_hw[l] = H[l]*W[l]); NULL, 0, NULL otherwise
+ *   smax        optional score summaries from cerb_decode for exactly these predictions, or NULL
  *   dets        out [T, B, max_det, 6] fp32 rows (x1, y1, x2, y2, conf, cls), score order;
  *               only the first counts[t*B + b] rows of a segment are written
  *   counts      out [T, B] int32
@@ -97,8 +97,8 @@ size_t cerb_nms_workspace_bytes(int T, int B, int max_det);
  */
 int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
              double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
-             int max_nms, double max_wh, const void* const* smax, int L, const int* level_hw, float* dets,
-             int* counts, void* workspace, size_t workspace_bytes, void* stream);
+             int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace,
+             size_t workspace_bytes, void* stream);
 
 /*
  * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy
