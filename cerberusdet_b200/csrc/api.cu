@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cerb_post.h"
@@ -90,6 +91,7 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
             while (vec > 1 && !aligned_to(p, vec * elt)) vec >>= 1;
         }
     }
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_VEC")) { int v = atoi(ev); if (v >= 1 && v < vec) vec = v; }  // tools/ only
     if (B == 0) return 0;
     // the score summary (one maximum per 16-byte score vector) needs the full 128-bit path
     if (smax != nullptr && vec == (int)(16 / elt)) {
@@ -100,7 +102,14 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
             if (summary_written) *summary_written = 1;
         }
     }
-    cudaError_t e = cerb_launch_decode(P, dtype, vec, (cudaStream_t)stream);
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    bool use_tma = vec == (int)(16 / elt);
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = use_tma && atoi(ev) != 0;  // tools/ only
+    if (use_tma) e = cerb_launch_decode_tma(P, dtype, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) {
+        (void)cudaGetLastError();
+        e = cerb_launch_decode(P, dtype, vec, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) {
         cerb_set_error("cerb_decode: launch failed: %s", cudaGetErrorString(e));
         return CERB_ECUDA;

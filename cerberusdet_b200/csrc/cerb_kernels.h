@@ -19,6 +19,8 @@ struct DecodeParams {
     void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V]: max of every 16-byte score vector
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
+// persistent TMA-pipelined variant; needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one
+cudaError_t cerb_launch_decode_tma(const DecodeParams& P, int dtype, cudaStream_t stream);
 
 // ------------------------------------------------------------------ select + NMS
 #define CERB_MAX_CLASS_WORDS 32  // class filter bitmask: nc <= 1024

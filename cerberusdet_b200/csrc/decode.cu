@@ -14,7 +14,12 @@
 // 512 contiguous bytes per channel.  Anchors are computed analytically.
 #include "cerb_kernels.h"
 
+#ifndef DEC_THREADS
 #define DEC_THREADS 128
+#endif
+#ifndef DEC_MINB
+#define DEC_MINB 1
+#endif
 #define CLS_CHUNK 32
 #define LOG2E_F 1.4426950408889634f
 
@@ -92,7 +97,7 @@ __device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const __grid_constant__ DecodeParams P) {
+__global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __grid_constant__ DecodeParams P) {
     // ---- block -> (row, part, vector block); uniform per block
     int row = 0;
     {

@@ -1,0 +1,130 @@
+"""Drop-in for the reference ``CerberusDetInference`` (cerberusdet/cerberusdet_inference.py:18-186).
+
+Same constructor and ``predict`` signatures, same attributes, same return structure
+(``List[List[Dict{box, score, label, label_name, task}]]``).  Inside, the per-task Python loop of
+the reference (``:125-135``: T calls of ``non_max_suppression``, each looping over the B images with
+~25 launches and ~4 host syncs per image) becomes: one decode launch for all task heads, one NMS
+launch for all (task, image) segments, one device->host copy.  The tail after NMS (``:140-184``) is
+host code (``cross_task.py``), as in the reference.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import cross_task
+from .detect import _RAW_FLAG
+from .ops import decode_heads, nms_batched
+
+
+@contextlib.contextmanager
+def raw_heads(model):
+    """While active, patched Detect heads return ``(None, levels)`` so that all task heads can be
+    decoded together in one launch."""
+    heads = [m for m in model.modules() if hasattr(type(m), "_cerb_reference_forward")]
+    for m in heads:
+        setattr(m, _RAW_FLAG, True)
+    try:
+        yield heads
+    finally:
+        for m in heads:
+            setattr(m, _RAW_FLAG, False)
+
+
+class CerberusDetInference:
+    def __init__(
+        self,
+        weights: Optional[str] = None,
+        device: str = "",
+        conf_thres: float = 0.25,
+        iou_thres: float = 0.45,
+        iou_thres_between_tasks: float = 0.8,
+        half: bool = False,
+        img_size: int = 640,
+        model=None,
+    ):
+        """``model=`` (extension): use an already built CerberusDet-like module instead of loading
+        ``weights`` -- anything whose forward returns ``{task: (pred_or_None, levels)}``."""
+        self.conf_thres = conf_thres
+        self.iou_thres = iou_thres
+        self.iou_thres_between_tasks = iou_thres_between_tasks
+        if model is None:
+            from . import patch
+
+            patch.install()
+            from cerberusdet.models.experimental import attempt_load  # reference loader (:37)
+            from cerberusdet.utils.general import check_img_size
+            from cerberusdet.utils.torch_utils import select_device
+
+            self.device = select_device(device)
+            model = attempt_load(weights, map_location=self.device)
+        else:
+            check_img_size = None
+            self.device = torch.device(device) if device else next(model.parameters()).device
+        self.half = half & (self.device.type != "cpu")
+        self.model = model
+        if self.half:
+            self.model.half()
+        self.model.eval()
+        self.stride = int(self.model.stride.max())
+        self.names: Dict[str, List[str]] = self.model.names if hasattr(self.model, "names") else self.model.module.names
+        self.categories_inds_map, self.all_class_names = cross_task.category_maps(self.names)
+        # warm-up forward, as in the reference (:51-54)
+        size = check_img_size(img_size, s=self.stride) if check_img_size else img_size
+        p = next(self.model.parameters())
+        self.model(torch.zeros(1, 3, size, size, device=self.device, dtype=p.dtype))
+
+    _get_categories_map = staticmethod(cross_task.category_maps)
+
+    def _head_strides(self, n_levels: int) -> List[float]:
+        for m in self.model.modules():
+            if hasattr(type(m), "_cerb_reference_forward") or type(m).__name__ == "Detect":
+                return [float(s) for s in m.stride]
+        return [float(s) for s in self.model.stride][:n_levels]
+
+    @torch.no_grad()
+    def predict(
+        self,
+        tensor: torch.Tensor,
+        original_shape: Union[Tuple[int, int], List[Tuple[int, int]], None] = None,
+        max_det: int = 300,
+        agnostic_nms: bool = False,
+        conf_thres: float = None,
+        iou_thres: float = None,
+        iou_thres_between_tasks: float = None,
+    ) -> List[List[Dict]]:
+        conf_thres = self.conf_thres if conf_thres is None else conf_thres
+        iou_thres = self.iou_thres if iou_thres is None else iou_thres
+        between = self.iou_thres_between_tasks if iou_thres_between_tasks is None else iou_thres_between_tasks
+
+        # 1. forward: every head hands over its raw per-level tensors
+        with raw_heads(self.model):
+            all_out = self.model(tensor)
+        tasks = list(all_out.keys())
+        preds = [all_out[t][0] for t in tasks]
+        if any(p is None for p in preds):  # raw mode was honoured: decode all heads in one launch
+            levels = [all_out[t][1] for t in tasks]
+            preds = decode_heads(levels, self._head_strides(len(levels[0])))
+        # 2. one NMS launch over all (task, image) segments; one D2H copy
+        dets, counts = nms_batched(preds, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det)
+        dets_h, counts_h = dets.cpu(), counts.cpu()
+
+        results = []
+        bsz = tensor.shape[0]
+        for i in range(bsz):
+            per_task = {t: dets_h[k, i, : int(counts_h[k, i])] for k, t in enumerate(tasks)}
+            det = cross_task.combine_tasks(per_task, self.categories_inds_map)
+            det = cross_task.suppress_between_tasks(det, self.categories_inds_map, between)
+            if len(det) > 0 and original_shape is not None:
+                shp = original_shape[i] if isinstance(original_shape, list) else original_shape
+                det[:, :4] = cross_task.rescale_boxes(tensor.shape[2:], det[:, :4], shp).round()
+            image_results = []
+            for *xyxy, conf, cls in det.tolist():
+                c = int(cls)
+                task_name = next((t for t, m in self.categories_inds_map.items() if c in m.values()), "unknown")
+                image_results.append({"box": [int(v) for v in xyxy], "score": float(conf), "label": c,
+                                      "label_name": self.all_class_names[c], "task": task_name})
+            results.append(image_results)
+        return results
