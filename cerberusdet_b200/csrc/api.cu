@@ -103,8 +103,10 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
         }
     }
     cudaError_t e = cudaErrorInvalidConfiguration;
-    bool use_tma = vec == (int)(16 / elt);
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = use_tma && atoi(ev) != 0;  // tools/ only
+    // The TMA-pipelined kernel (decode_tma.cu) is kept as a measured alternative; the register-resident kernel is
+    // faster on B200 for both dtypes (profiles/r01_decode.md), so it is the default.
+    bool use_tma = false;
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = vec == (int)(16 / elt) && atoi(ev) != 0;  // tools/ only
     if (use_tma) e = cerb_launch_decode_tma(P, dtype, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) {
         (void)cudaGetLastError();

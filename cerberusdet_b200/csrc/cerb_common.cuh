@@ -26,14 +26,58 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
 __device__ __forceinline__ float fast_ex2(float x) {
+#ifdef CERB_EXPERIMENT_NO_MUFU  // tools/ only: where does the time go without the SFU?
+    return x * 0.5f + 1.0f;
+#else
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 __device__ __forceinline__ float fast_rcp(float x) {
+#ifdef CERB_EXPERIMENT_NO_MUFU
+    return 2.0f - x;
+#else
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
+}
+
+// Expected DFL distance of one box side: sum_k k * softmax(x)_k over the 16 bins (reference DFL.forward,
+// models/yolo.py:57-59).  Rounding points follow the reference for half tensors: probabilities are rounded
+// to half (softmax output), the frozen 1x1 conv accumulates in fp32 and rounds once.  Max, sum and the
+// weighted sum are evaluated as short trees / 4 partial sums so the 16 bins give instruction-level
+// parallelism instead of three 16-long dependency chains.
+#define CERB_LOG2E 1.4426950408889634f
+template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x)[CERB_REG_MAX]) {
+#ifdef CERB_EXPERIMENT_COPY_ONLY  // tools/ only: memory floor of this access pattern
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < CERB_REG_MAX; ++k) t += x[k];
+    return t;
+#endif
+    float m0 = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    float m1 = fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]));
+    float m2 = fmaxf(fmaxf(x[8], x[9]), fmaxf(x[10], x[11]));
+    float m3 = fmaxf(fmaxf(x[12], x[13]), fmaxf(x[14], x[15]));
+    const float mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * CERB_LOG2E;
+#pragma unroll
+    for (int k = 0; k < CERB_REG_MAX; ++k) x[k] = fast_ex2(fmaf(x[k], CERB_LOG2E, -mb));
+    const float s0 = (x[0] + x[1]) + (x[2] + x[3]);
+    const float s1 = (x[4] + x[5]) + (x[6] + x[7]);
+    const float s2 = (x[8] + x[9]) + (x[10] + x[11]);
+    const float s3 = (x[12] + x[13]) + (x[14] + x[15]);
+    const float inv = fast_rcp((s0 + s1) + (s2 + s3));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CERB_REG_MAX; k += 4) {
+        a0 = fmaf((float)k, rnd<T>(x[k] * inv), a0);
+        a1 = fmaf((float)(k + 1), rnd<T>(x[k + 1] * inv), a1);
+        a2 = fmaf((float)(k + 2), rnd<T>(x[k + 2] * inv), a2);
+        a3 = fmaf((float)(k + 3), rnd<T>(x[k + 3] * inv), a3);
+    }
+    return rnd<T>((a0 + a1) + (a2 + a3));
 }
 
 // streaming 128-bit / 64-bit / scalar accesses (read once, write once: keep them out of L1)

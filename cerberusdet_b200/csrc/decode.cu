@@ -18,7 +18,7 @@
 #define DEC_THREADS 128
 #endif
 #ifndef DEC_MINB
-#define DEC_MINB 1
+#define DEC_MINB 5  // 96 registers -> 20 warps per SM: best of the measured variants (profiles/r01_decode.md)
 #endif
 #define CLS_CHUNK 32
 #define LOG2E_F 1.4426950408889634f
@@ -75,24 +75,9 @@ __device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         float x[CERB_REG_MAX];
-        float m = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < CERB_REG_MAX; ++k) {
-            x[k] = to_f32<T>(v[k].e[i]);
-            m = fmaxf(m, x[k]);
-        }
-        const float mb = m * LOG2E_F;
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < CERB_REG_MAX; ++k) {
-            x[k] = fast_ex2(fmaf(x[k], LOG2E_F, -mb));
-            s += x[k];
-        }
-        const float inv = fast_rcp(s);
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 1; k < CERB_REG_MAX; ++k) acc = fmaf((float)k, rnd<T>(x[k] * inv), acc);
-        d[i] = rnd<T>(acc);
+        for (int k = 0; k < CERB_REG_MAX; ++k) x[k] = to_f32<T>(v[k].e[i]);
+        d[i] = dfl_expectation<T>(x);
     }
 }
 
@@ -130,6 +115,16 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
     if (part < 2) {
         // sides (l, r) -> cx, w   or   (t, b) -> cy, h      (utils/tal.py:198-204)
         float dlo[VEC], dhi[VEC];
+#ifdef CERB_L2_PREFETCH  // measured slower on B200 (profiles/r01_decode.md); kept for the record
+        // while the first side is being reduced nothing of this warp is in flight: pull the second side's
+        // rows into L2 meanwhile (one 128-byte line per 128 / (16) lanes)
+        if (sizeof(T) * VEC == 16 && (threadIdx.x & 7) == 0) {
+            const T* nxt = in + (size_t)((part + 2) * CERB_REG_MAX) * hw;
+#pragma unroll
+            for (int k = 0; k < CERB_REG_MAX; ++k)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)k * hw));
+        }
+#endif
         dfl_side<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, dlo);
         dfl_side<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, dhi);
         const int W = P.w[level];

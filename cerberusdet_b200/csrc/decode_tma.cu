@@ -2,29 +2,33 @@
 // tensors allow 16-byte rows; decode.cu is the generic fallback and the comparison point).
 //
 // Why: the register-resident kernel in decode.cu is latency bound -- a warp first waits for its 16
-// loads, then spends ~7000 cycles on exp/rcp work with nothing in flight, and at 146 registers only
-// 12 warps fit on an SM, so on average ~20 KB per SM are in flight where HBM3e needs ~45 KB
-// (profiles/r01_decode_v1.md).  Here one producer warp per SM streams [64+nc] x TA tiles into a
-// shared-memory ring with cp.async.bulk (TMA, mbarrier complete_tx) several tiles ahead of the 16
-// consumer warps, which only ever touch shared memory.
+// loads, then spends thousands of cycles on exp/rcp work with nothing in flight, and at ~100-146
+// registers only 12-20 warps fit on an SM, so on average ~20 KB per SM are in flight where HBM3e
+// needs ~45 KB (profiles/r01_decode.md).  Here one producer warp per SM streams [64+nc] x TA
+// tiles into a shared-memory ring with cp.async.bulk (TMA, mbarrier complete_tx) several tiles ahead
+// of the 15 consumer warps, which only ever read shared memory.
 //
 // Same arithmetic and rounding points as decode.cu (reference models/yolo.py:93-99, utils/tal.py).
 //
 // Tile = TA consecutive anchors of one (task, level, image), all 64+nc channels: TA = 256 (fp16) or
-// 128 (fp32), i.e. 512-byte rows, one bulk copy per channel row.  Consumer thread (p, q): p = anchor
-// pair (fp16) / anchor (fp32) inside the tile, q = quarter: DFL side q (l, t, r, b) plus a quarter of the
-// class channels.  Sides meet through a small shared scratch (one named barrier per tile): q = 0
-// finishes (cx, w), q = 1 finishes (cy, h).
+// 128 (fp32), i.e. 512-byte rows, one bulk copy per channel row.  A consumer warp owns one role of one
+// tile -- lane = 16 bytes of anchors: role 0 = DFL sides l,r -> (cx, w); role 1 = sides t,b -> (cy, h);
+// role 2 = class sigmoids + score summary.  The 15 consumer warps form 5 groups of 3 roles; group g
+// takes the CTA's tiles k = g, g+5, ...; warps never synchronise with each other, only with the
+// stage's full/empty mbarriers, so light roles run ahead inside the ring.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "cerb_kernels.h"
 
-#define TMA_CONSUMER_WARPS 16
-#define TMA_CONSUMERS (TMA_CONSUMER_WARPS * 32)
-#define TMA_THREADS (TMA_CONSUMERS + 32)
-#define TMA_PAIRS 128  // consumer threads per quarter
+#define TMA_ROLES 3
+#define TMA_GROUPS 5
+#define TMA_CONSUMER_WARPS (TMA_ROLES * TMA_GROUPS)
+#define TMA_THREADS ((TMA_CONSUMER_WARPS + 1) * 32)
 #define TMA_MAX_STAGES 8
 #define LOG2E_F 1.4426950408889634f
 
 struct TmaDecodeParams {
+    CUtensorMap maps[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // one 2-D map per (task, level): [B*no rows, hw cols]
     DecodeParams d;
     int tiles_per_image[CERB_MAX_LEVELS];
     int row_tile_start[CERB_MAX_TASKS * CERB_MAX_LEVELS + 1];  // first tile of each (task, level) row
@@ -55,30 +59,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+// one TMA op moves the whole [no x TA] box of a tile (out-of-range columns are zero-filled and counted)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
+template <typename T> union Vec16 {
+    uint4 raw;
+    T e[16 / sizeof(T)];
+};
 
-// LW elements (4 bytes) of one channel row as floats
-template <typename T> struct Lane;
-template <> struct Lane<__half> {
-    static constexpr int LW = 2;
-    __device__ static __forceinline__ void load(const void* p, float (&x)[2]) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(p));
-        x[0] = f.x; x[1] = f.y;
+// Expected DFL distance of one box side for the V anchors of this lane, read from the staged tile.
+template <typename T>
+__device__ __forceinline__ void dfl_side_smem(const unsigned char* side_base, int row_bytes, float (&d)[16 / sizeof(T)]) {
+    constexpr int V = 16 / sizeof(T);
+    Vec16<T> v[CERB_REG_MAX];
+#pragma unroll
+    for (int k = 0; k < CERB_REG_MAX; ++k) v[k].raw = *reinterpret_cast<const uint4*>(side_base + (size_t)k * row_bytes);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        float x[CERB_REG_MAX];
+#pragma unroll
+        for (int k = 0; k < CERB_REG_MAX; ++k) x[k] = to_f32<T>(v[k].e[i]);
+        d[i] = dfl_expectation<T>(x);
     }
-    __device__ static __forceinline__ void store(void* p, const float (&x)[2]) {
-        *reinterpret_cast<__half2*>(p) = __floats2half2_rn(x[0], x[1]);
-    }
-};
-template <> struct Lane<float> {
-    static constexpr int LW = 1;
-    __device__ static __forceinline__ void load(const void* p, float (&x)[1]) { x[0] = *reinterpret_cast<const float*>(p); }
-    __device__ static __forceinline__ void store(void* p, const float (&x)[1]) { *reinterpret_cast<float*>(p) = x[0]; }
-};
+}
 
 struct TileInfo { int task, level, b, a0, cnt; };
 
@@ -101,19 +108,18 @@ __device__ __forceinline__ TileInfo locate_tile(const TmaDecodeParams& P, int t,
 
 template <typename T>
 __global__ void __launch_bounds__(TMA_THREADS, 1) decode_tma_kernel(const __grid_constant__ TmaDecodeParams P) {
-    constexpr int LW = Lane<T>::LW;
-    constexpr int TA = TMA_PAIRS * LW;  // anchors per tile
-    constexpr int V = 16 / sizeof(T);   // anchors per summary entry
+    constexpr int V = 16 / sizeof(T);  // anchors per lane
+    constexpr int TA = 32 * V;         // anchors per tile
+    constexpr int ROWB = TA * (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TMA_MAX_STAGES];
-    __shared__ float dscr[2][4][TA];  // DFL distances of the four sides, double buffered by tile parity
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int stages = P.stages;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);                                    // full: producer's expect_tx arrive
-            mbar_init(smem_u32(&bars[TMA_MAX_STAGES + s]), TMA_CONSUMER_WARPS);  // empty: one arrive per consumer warp
+            mbar_init(smem_u32(&bars[s]), 1);                            // full: producer's expect_tx arrive
+            mbar_init(smem_u32(&bars[TMA_MAX_STAGES + s]), TMA_ROLES);   // empty: one arrive per role warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -128,133 +134,150 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) decode_tma_kernel(const __grid
             mbar_wait(smem_u32(&bars[TMA_MAX_STAGES + s]), (use & 1u) ^ 1u);
             const TileInfo ti = locate_tile(P, t, TA);
             const int no = 4 * CERB_REG_MAX + P.d.nc[ti.task];
-            const int hw = P.d.hw[ti.level];
-            const uint32_t row_bytes = (uint32_t)(ti.cnt * sizeof(T));
             const uint32_t full = smem_u32(&bars[s]);
-            if (lane == 0) mbar_arrive_expect_tx(full, row_bytes * (uint32_t)no);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full, (uint32_t)(no * ROWB));
+                tma_load_2d(smem_u32(smem + (size_t)s * P.stage_bytes), &P.maps[ti.task * P.d.L + ti.level], ti.a0,
+                            ti.b * no, full);
+            }
             __syncwarp();
-            const T* src = reinterpret_cast<const T*>(P.d.lvl[ti.task][ti.level]) + (size_t)ti.b * no * hw + ti.a0;
-            const uint32_t dst = smem_u32(smem + (size_t)s * P.stage_bytes);
-            for (int r = lane; r < no; r += 32)
-                bulk_g2s(dst + (uint32_t)(r * TA * sizeof(T)), src + (size_t)r * hw, row_bytes, full);
         }
         return;
     }
 
     // ---------------------------------------------------- consumers
-    const int q = wid >> 2;                  // quarter: DFL side q + a quarter of the classes
-    const int p = (wid & 3) * 32 + lane;     // lane-column inside the tile
-    int k = 0;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++k) {
+    const int group = wid / TMA_ROLES, role = wid - group * TMA_ROLES;
+    for (int k = group, t = blockIdx.x + group * gridDim.x; t < P.ntiles; k += TMA_GROUPS, t += TMA_GROUPS * gridDim.x) {
         const int s = k % stages;
         const uint32_t use = (uint32_t)(k / stages);
         const TileInfo ti = locate_tile(P, t, TA);
         const int nc = P.d.nc[ti.task];
         const int A = P.d.A;
-        const int al = p * LW;                       // first anchor of this thread inside the tile
-        const bool live = al < ti.cnt;               // cnt is a multiple of V >= LW: whole lanes are live or not
-        const unsigned char* st = smem + (size_t)s * P.stage_bytes + (size_t)al * sizeof(T);
+        const int al = lane * V;        // first anchor of this lane inside the tile
+        const bool live = al < ti.cnt;  // cnt is a multiple of V: a lane is entirely live or not
+        const unsigned char* st = smem + (size_t)s * P.stage_bytes + (size_t)lane * 16;
         T* __restrict__ out = reinterpret_cast<T*>(P.d.y[ti.task]) + (size_t)ti.b * (4 + nc) * A + P.d.aoff[ti.level] + ti.a0 + al;
 
         mbar_wait(smem_u32(&bars[s]), use & 1u);
-
-        // ---- DFL side q: expectation of softmax over the 16 bins (reference models/yolo.py:57-59)
-        float d[LW];
-        {
-            float x[CERB_REG_MAX][LW];
-            float m[LW];
-#pragma unroll
-            for (int i = 0; i < LW; ++i) m[i] = -INFINITY;
-#pragma unroll
-            for (int kk = 0; kk < CERB_REG_MAX; ++kk) {
-                Lane<T>::load(st + (size_t)(q * CERB_REG_MAX + kk) * TA * sizeof(T), x[kk]);
-#pragma unroll
-                for (int i = 0; i < LW; ++i) m[i] = fmaxf(m[i], x[kk][i]);
+        if (role < 2) {
+            // sides (l, r) -> cx, w   or   (t, b) -> cy, h      (utils/tal.py:198-204)
+            float dlo[V], dhi[V];
+            if (live) {
+                dfl_side_smem<T>(st + (size_t)(role * CERB_REG_MAX) * ROWB, ROWB, dlo);
+                dfl_side_smem<T>(st + (size_t)((role + 2) * CERB_REG_MAX) * ROWB, ROWB, dhi);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[TMA_MAX_STAGES + s]));  // stage no longer needed by this warp
+            if (live) {
+                const int W = P.d.w[ti.level];
+                const float stride = P.d.stride[ti.level];
+                Vec16<T> oc, os;
 #pragma unroll
-            for (int i = 0; i < LW; ++i) {
-                const float mb = m[i] * LOG2E_F;
-                float ssum = 0.f;
-#pragma unroll
-                for (int kk = 0; kk < CERB_REG_MAX; ++kk) {
-                    x[kk][i] = fast_ex2(fmaf(x[kk][i], LOG2E_F, -mb));
-                    ssum += x[kk][i];
+                for (int i = 0; i < V; ++i) {
+                    const int a = ti.a0 + al + i;
+                    const int g = (role == 0) ? (a % W) : (a / W);
+                    const float ac = rnd<T>(rnd<T>((float)g) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
+                    const float p1 = rnd<T>(ac - dlo[i]);
+                    const float p2 = rnd<T>(ac + dhi[i]);
+                    const float c = rnd<T>(rnd<T>(p1 + p2) * 0.5f);
+                    const float sz = rnd<T>(p2 - p1);
+                    oc.e[i] = from_f32<T>(c * stride);
+                    os.e[i] = from_f32<T>(sz * stride);
                 }
-                const float inv = fast_rcp(ssum);
-                float acc = 0.f;
-#pragma unroll
-                for (int kk = 1; kk < CERB_REG_MAX; ++kk) acc = fmaf((float)kk, rnd<T>(x[kk][i] * inv), acc);
-                d[i] = rnd<T>(acc);
+                stg_stream16(out + (size_t)role * A, oc.raw);
+                stg_stream16(out + (size_t)(role + 2) * A, os.raw);
             }
-        }
-#pragma unroll
-        for (int i = 0; i < LW; ++i) dscr[k & 1][q][al + i] = d[i];
-
-        // ---- this thread's quarter of the class channels: sigmoid (yolo.py:99) + score summary
-        {
-            const int cq = (nc + 3) >> 2;
-            const int c0 = q * cq, c1 = min(nc, c0 + cq);
+        } else {
+            // class sigmoids (yolo.py:99) + score summary (max of each 16-byte score vector)
             const size_t srow = ((size_t)(A / V) + V - 1) / V * V;
             T* smx = nullptr;
             if (P.d.smax[ti.task] != nullptr)
                 smx = reinterpret_cast<T*>(P.d.smax[ti.task]) + (size_t)ti.b * nc * srow + (P.d.aoff[ti.level] + ti.a0 + al) / V;
-            const bool writer = (lane % (V / LW)) == 0;
-            for (int c = c0; c < c1; ++c) {
-                float sc[LW];
-                float mx = -INFINITY;
-                if (live) {
-                    Lane<T>::load(st + (size_t)(4 * CERB_REG_MAX + c) * TA * sizeof(T), sc);
+            if (live) {
+                const unsigned char* cls = st + (size_t)(4 * CERB_REG_MAX) * ROWB;
+                T* cout = out + (size_t)4 * A;
+                int c = 0;
+                for (; c + 4 <= nc; c += 4) {
+                    Vec16<T> vv[4];
 #pragma unroll
-                    for (int i = 0; i < LW; ++i) {
-                        sc[i] = rnd<T>(fast_rcp(1.f + fast_ex2(-sc[i] * LOG2E_F)));
-                        mx = fmaxf(mx, sc[i]);
+                    for (int u = 0; u < 4; ++u) vv[u].raw = *reinterpret_cast<const uint4*>(cls + (size_t)(c + u) * ROWB);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                            const float x = to_f32<T>(vv[u].e[i]);
+                            vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                            mx = fmaxf(mx, to_f32<T>(vv[u].e[i]));
+                        }
+                        stg_stream16(cout + (size_t)(c + u) * A, vv[u].raw);
+                        if (smx != nullptr) smx[(size_t)(c + u) * srow] = from_f32<T>(mx);
                     }
-                    Lane<T>::store(out + (size_t)(4 + c) * A, sc);
                 }
-                if (P.d.smax[ti.task] != nullptr) {
+                for (; c < nc; ++c) {
+                    Vec16<T> v1;
+                    v1.raw = *reinterpret_cast<const uint4*>(cls + (size_t)c * ROWB);
+                    float mx = -INFINITY;
 #pragma unroll
-                    for (int o = 1; o < V / LW; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    if (live && writer) smx[(size_t)c * srow] = from_f32<T>(mx);
+                    for (int i = 0; i < V; ++i) {
+                        const float x = to_f32<T>(v1.e[i]);
+                        v1.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
+                        mx = fmaxf(mx, to_f32<T>(v1.e[i]));
+                    }
+                    stg_stream16(cout + (size_t)c * A, v1.raw);
+                    if (smx != nullptr) smx[(size_t)c * srow] = from_f32<T>(mx);
                 }
             }
-        }
-        // all reads of the stage are done: hand it back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[TMA_MAX_STAGES + s]));
-
-        // ---- sides meet: q = 0 finishes (cx, w) from (l, r), q = 1 finishes (cy, h) from (t, b)
-        consumer_bar();
-        if (q < 2 && live) {
-            const int W = P.d.w[ti.level];
-            const float stride = P.d.stride[ti.level];
-            float oc[LW], os[LW];
-#pragma unroll
-            for (int i = 0; i < LW; ++i) {
-                const int a = ti.a0 + al + i;
-                const int g = (q == 0) ? (a % W) : (a / W);
-                const float ac = rnd<T>(rnd<T>((float)g) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
-                const float p1 = rnd<T>(ac - dscr[k & 1][q][al + i]);
-                const float p2 = rnd<T>(ac + dscr[k & 1][q + 2][al + i]);
-                oc[i] = rnd<T>(rnd<T>(rnd<T>(p1 + p2) * 0.5f) * stride);  // utils/tal.py:198-204, yolo.py:98
-                os[i] = rnd<T>(rnd<T>(p2 - p1) * stride);
-            }
-            Lane<T>::store(out + (size_t)q * A, oc);
-            Lane<T>::store(out + (size_t)(q + 2) * A, os);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[TMA_MAX_STAGES + s]));
         }
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 template <typename T> static cudaError_t launch_tma_t(const DecodeParams& D, cudaStream_t stream) {
-    constexpr int TA = TMA_PAIRS * Lane<T>::LW;
+    constexpr int TA = 32 * (16 / (int)sizeof(T));
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return cudaErrorInvalidConfiguration;
     TmaDecodeParams P;
     P.d = D;
     int tiles = 0, no_max = 0;
     for (int l = 0; l < D.L; ++l) P.tiles_per_image[l] = (D.hw[l] + TA - 1) / TA;
     for (int t = 0; t < D.T; ++t) {
-        no_max = max(no_max, 4 * CERB_REG_MAX + D.nc[t]);
+        const int no = 4 * CERB_REG_MAX + D.nc[t];
+        if (no > 256) return cudaErrorInvalidConfiguration;  // TMA box rows <= 256: wide heads use the generic kernel
+        no_max = max(no_max, no);
         for (int l = 0; l < D.L; ++l) {
             P.row_tile_start[t * D.L + l] = tiles;
             tiles += D.B * P.tiles_per_image[l];
+            const cuuint64_t gdim[2] = {(cuuint64_t)D.hw[l], (cuuint64_t)D.B * (cuuint64_t)no};
+            const cuuint64_t gstride[1] = {(cuuint64_t)D.hw[l] * sizeof(T)};
+            const cuuint32_t box[2] = {(cuuint32_t)TA, (cuuint32_t)no};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = encode(&P.maps[t * D.L + l],
+                                      sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                      const_cast<void*>(D.lvl[t][l]), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return cudaErrorInvalidConfiguration;
         }
     }
     P.row_tile_start[D.nrows] = tiles;
@@ -265,7 +288,7 @@ template <typename T> static cudaError_t launch_tma_t(const DecodeParams& D, cud
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int static_smem = 2 * 4 * TA * 4 + 2 * TMA_MAX_STAGES * 8 + 256;
+    const int static_smem = 2 * TMA_MAX_STAGES * 8 + 1024;
     int stages = (smem_max - static_smem) / P.stage_bytes;
     if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
     if (stages < 2) return cudaErrorInvalidConfiguration;  // caller falls back to the generic kernel

@@ -1,11 +1,10 @@
 import os, sys, subprocess, json
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = [("default", None, None)] + [(f"t{t}_b{b}", f"{root}/cerberusdet_b200/libcerb_dec_{t}_{b}.so", None) for t, b in [(128,4),(128,5),(256,2),(256,3),(64,8)]]
-variants += [("default_vec4", None, "4"), ("t128_b5_vec4", f"{root}/cerberusdet_b200/libcerb_dec_128_5.so", "4"), ("t256_b3_vec4", f"{root}/cerberusdet_b200/libcerb_dec_256_3.so", "4")]
-for name, lib, vec in variants:
+variants = [("default(prefetch,b5)", None), ("no_prefetch_b5", "libcerb_nopf.so"), ("prefetch_b3", "libcerb_pf_b3.so"), ("prefetch_b4", "libcerb_pf_b4.so"), ("prefetch_b6", "libcerb_pf_b6.so")]
+for name, lib in variants:
     env = dict(os.environ)
-    if lib: env["CERB_LIB"] = lib
-    if vec: env["CERB_DEBUG_DECODE_VEC"] = vec
-    out = subprocess.run([sys.executable, f"{root}/tools/microbench.py", "cfg3"], env=env, capture_output=True, text=True).stdout.strip().splitlines()
-    d = json.loads(out[-1]) if out else {}
-    print(name, d.get("decode_us_med"), d.get("decode_us_min"), d.get("decode_GBps_med"), flush=True)
+    if lib: env["CERB_LIB"] = f"{root}/cerberusdet_b200/{lib}"
+    out = subprocess.run([sys.executable, f"{root}/tools/microbench.py", "cfg3", "cfg3f32"], env=env, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out[-2:]:
+        d = json.loads(line)
+        print(name, d["cfg"], d.get("decode_us_med"), d.get("decode_us_min"), d.get("decode_GBps_med"), flush=True)
