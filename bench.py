@@ -53,26 +53,60 @@ def _decode_bytes_per_image(ncs, anchors, elt):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """SM clock + throttle reasons of one GPU while the timed region runs (NVML, ~2 ms period;
+    falls back to polling nvidia-smi)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop = threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = self.index
+        if vis:
+            try:
+                phys = int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                phys = self.index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+            for name, bit in self.BAD.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            self.stop.wait(0.002)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.sm.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    self.reasons.update(n for i, n in enumerate(names) if parts[2 + i].lower().startswith("active"))
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self.th.start()
@@ -83,14 +117,10 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def cpu_port_segment(heads_cpu, image, task):
@@ -156,8 +186,8 @@ def _config(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -267,7 +297,7 @@ def main():
                          "nms_ms_avg": sum(nms_ms) / len(nms_ms), "nms_ms_median": statistics.median(nms_ms)},
             "e2e": {"value": B_PER_GPU * world * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 2 * args.steps,  # decode_kernel + nms_kernel per step, nothing else
             "clocks": clk.summary(),
         }
         if not args.no_cpu_baseline:

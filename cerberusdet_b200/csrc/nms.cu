@@ -924,6 +924,8 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
     }
 
     if (tid == 0) P.counts[seg] = kept;
+    // rows past the count are zero so the padded [T, B, max_det, 6] output is deterministic without a separate fill
+    for (int i = kept * 6 + tid; i < max_det * 6; i += NMS_THREADS) dets[i] = 0.f;
     PROF(9);  // rest
 #ifdef NMS_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0) { g_nms_prof[10] += 1; g_nms_prof[11] += consumed; }

@@ -36,8 +36,7 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-@torch.library.custom_op("cerb::decode", mutates_args=())
-def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
+def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
     """Returns ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``; the score summaries ``smax_t`` are empty
     tensors when the shapes do not allow them (see include/cerb_post.h)."""
     lib = _lib.load()
@@ -80,6 +79,12 @@ def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequen
     return ys + sm
 
 
+@torch.library.custom_op("cerb::decode", mutates_args=())
+def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
+    """torch custom op over ``_decode_impl`` (for graphs / compile); the Python wrappers call the impl directly."""
+    return _decode_impl(levels, nc, strides)
+
+
 @decode_op.register_fake
 def _(levels, nc, strides):
     T = len(nc)
@@ -92,8 +97,7 @@ def _(levels, nc, strides):
         levels[0].new_empty((B, nc[t], R)) for t in range(T)]
 
 
-@torch.library.custom_op("cerb::nms", mutates_args=())
-def nms_op(
+def _nms_impl(
     preds: Sequence[torch.Tensor],
     conf_thres: float,
     iou_thres: float,
@@ -118,8 +122,8 @@ def nms_op(
         ncs.append(int(p.shape[1]) - 4)
         ps.append(p.contiguous())
     dev = first.device
-    dets = torch.zeros((T, B, max_det, 6), dtype=torch.float32, device=dev)
-    counts = torch.zeros((T, B), dtype=torch.int32, device=dev)
+    dets = torch.empty((T, B, max_det, 6), dtype=torch.float32, device=dev)  # the kernel writes every row
+    counts = torch.empty((T, B), dtype=torch.int32, device=dev)
     ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     cls_arr = _lib.int_array(list(classes)) if classes is not None else None
@@ -142,6 +146,23 @@ def nms_op(
         )
     _lib.check(rc)
     return dets, counts
+
+
+@torch.library.custom_op("cerb::nms", mutates_args=())
+def nms_op(
+    preds: Sequence[torch.Tensor],
+    conf_thres: float,
+    iou_thres: float,
+    classes: Optional[Sequence[int]],
+    agnostic: bool,
+    multi_label: bool,
+    max_det: int,
+    max_nms: int,
+    max_wh: float,
+    smax: Sequence[torch.Tensor],
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """torch custom op over ``_nms_impl``."""
+    return _nms_impl(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax)
 
 
 @nms_op.register_fake
@@ -189,7 +210,7 @@ def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequenc
     The kernel also leaves a score summary per task, remembered for ``nms_batched``."""
     flat = [x for lv in task_levels for x in lv]
     nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
-    out = decode_op(flat, nc, [float(s) for s in strides])
+    out = _decode_impl(flat, nc, [float(s) for s in strides])
     T = len(nc)
     ys, sms = out[:T], out[T:]
     for y, sm in zip(ys, sms):
@@ -222,6 +243,6 @@ def nms_batched(
         found = [find_summary(p) for p in preds]
         if all(f is not None for f in found):
             smax = found
-    return nms_op(preds, float(conf_thres), float(iou_thres),
+    return _nms_impl(preds, float(conf_thres), float(iou_thres),
                   None if classes is None else [int(c) for c in classes],
                   bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)

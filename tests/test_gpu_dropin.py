@@ -1,0 +1,137 @@
+"""GPU tests of the drop-in surfaces (Detect.forward replacement, CerberusDetInference mirror) on a
+stand-in model with the reference's head interface.  /root/reference is not available on the GPU box, so
+the stand-in Detect class reproduces only the attributes the drop-in touches; its own forward is the
+oracle's torch restatement of the reference eval branch."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from cerberusdet_b200.synth import STRIDES
+from tol import check_decode
+
+pytestmark = pytest.mark.gpu
+
+
+class Detect(nn.Module):
+    dynamic = False
+    export = False
+    shape = None
+    anchors = torch.empty(0)
+    strides = torch.empty(0)
+
+    def __init__(self, nc, ch):
+        super().__init__()
+        self.nc, self.nl, self.reg_max = nc, len(ch), 16
+        self.no = nc + 64
+        self.stride = torch.tensor(STRIDES)
+        self.cv2 = nn.ModuleList(nn.Conv2d(c, 64, 1) for c in ch)
+        self.cv3 = nn.ModuleList(nn.Conv2d(c, nc, 1) for c in ch)
+
+    def forward(self, x):  # torch restatement of reference models/yolo.py:87-100 (oracle code path)
+        from oracle import ref_port as rp
+
+        for i in range(self.nl):
+            x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i])), 1)
+        if self.training:
+            return x
+        y = rp.decode_port(x, self.nc, [float(s) for s in self.stride])
+        return y if self.export else (y, x)
+
+
+class TwoTaskModel(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.stem = nn.Conv2d(3, 8, 3, padding=1)
+        self.heads = nn.ModuleDict({"voc": Detect(20, (8, 8, 8)), "animals": Detect(19, (8, 8, 8))})
+        self.names = {"voc": [f"v{i}" for i in range(20)], "animals": [f"a{i}" for i in range(19)]}
+        self.stride = torch.tensor(STRIDES)
+        for h in self.heads.values():  # spread the class logits so a few hundred candidates pass
+            for m in h.cv3:
+                nn.init.normal_(m.weight, std=1.5)
+                nn.init.constant_(m.bias, -3.0)
+            for m in h.cv2:
+                nn.init.normal_(m.weight, std=1.0)
+
+    def forward(self, x):
+        f = self.stem(x)
+        feats = [nn.functional.avg_pool2d(f, int(s)) for s in STRIDES]
+        return {t: h([z.clone() for z in feats]) for t, h in self.heads.items()}
+
+
+@pytest.fixture()
+def patched():
+    from cerberusdet_b200.detect import detect_forward
+
+    Detect._cerb_reference_forward = Detect.forward
+    orig = Detect.forward
+    Detect.forward = detect_forward
+    yield
+    Detect.forward = orig
+    del Detect._cerb_reference_forward
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_detect_forward_dropin(patched, half):
+    torch.manual_seed(0)
+    head = Detect(12, (8, 8, 8)).cuda().eval()
+    if half:
+        head.half()
+    dt = torch.float16 if half else torch.float32
+    feats = [torch.randn(2, 8, 32 // k, 48 // k, device="cuda", dtype=dt) for k in (1, 2, 4)]
+    with torch.no_grad():
+        y, x = head([f.clone() for f in feats])                       # B200 path
+        y_ref, x_ref = Detect._cerb_reference_forward(head, [f.clone() for f in feats])  # torch path, same convs
+    assert y.dtype == dt and tuple(y.shape) == (2, 16, 32 * 48 + 16 * 24 + 8 * 12)
+    assert all(torch.equal(a, b) for a, b in zip(x, x_ref))           # the list holds the raw per-level tensors
+    ok, msg = check_decode(y, y_ref.cpu() if False else y_ref, [t.shape[2:] for t in x], STRIDES, 12)
+    assert ok, msg
+    assert head.shape == feats[0].shape and tuple(head.anchors.shape) == (2, y.shape[2]) and tuple(head.strides.shape) == (1, y.shape[2])
+    head.export = True
+    with torch.no_grad():
+        assert torch.equal(head([f.clone() for f in feats]), y)
+    head.export = False
+    head.train()
+    out = head([f.clone() for f in feats])                            # training branch untouched: list of raw tensors
+    assert isinstance(out, list) and len(out) == 3
+    cpu_head = copy.deepcopy(head).float().cpu().eval()               # CPU tensors run the class's own forward
+    with torch.no_grad():
+        y_cpu, _ = cpu_head([f.float().cpu() for f in feats])
+    assert not y_cpu.is_cuda
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_inference_mirror_matches_oracle_pipeline(patched, half):
+    from cerberusdet_b200 import cross_task as ct
+    from cerberusdet_b200.inference import CerberusDetInference
+    from oracle import ref_port as rp
+
+    torch.manual_seed(1)
+    model = TwoTaskModel().cuda()
+    eng = CerberusDetInference(model=model, device="cuda:0", conf_thres=0.25, iou_thres=0.45, half=half, img_size=64)
+    assert eng.stride == 32 and len(eng.all_class_names) == 39 and eng.categories_inds_map["animals"][3] == 23
+    x = torch.rand(3, 3, 96, 128, device="cuda")
+    x = x.half() if half else x
+    got = eng.predict(x, original_shape=[(480, 640), (96, 128), (300, 500)], max_det=50)
+    assert len(got) == 3
+
+    # oracle pipeline on the same conv outputs: decode on the GPU path is checked elsewhere; here selection
+    # must be identical given the same decoded tensors, so feed the oracle NMS with the drop-in's own y
+    with torch.no_grad():
+        out = eng.model(x)
+    per_task = {}
+    for t, (y, _) in out.items():
+        per_task[t] = rp.nms_port(y.cpu(), 0.25, 0.45, max_det=50, greedy="c")
+    for i in range(3):
+        det = ct.combine_tasks({t: per_task[t][i] for t in per_task}, eng.categories_inds_map)
+        det = ct.suppress_between_tasks(det, eng.categories_inds_map, 0.8)
+        if len(det):
+            det[:, :4] = ct.rescale_boxes((96, 128), det[:, :4], [(480, 640), (96, 128), (300, 500)][i]).round()
+        want = [{"box": [int(v) for v in r[:4]], "score": float(r[4]), "label": int(r[5])} for r in det.tolist()]
+        assert len(got[i]) == len(want)
+        for g, w in zip(got[i], want):
+            assert g["box"] == w["box"] and g["label"] == w["label"] and g["score"] == w["score"]
+            assert g["label_name"] == eng.all_class_names[g["label"]]
+            assert g["task"] == ("voc" if g["label"] < 20 else "animals")
+    assert sum(len(r) for r in got) > 0
