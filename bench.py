@@ -205,7 +205,7 @@ def main():
 
     from cerberusdet_b200 import ops
     from cerberusdet_b200.api import postprocess_host
-    from cerberusdet_b200.shard import gather_detections
+    from cerberusdet_b200.shard import DetectionGatherer
     from cerberusdet_b200.synth import STRIDES, synth_heads
 
     torch.cuda.set_device(local_rank)
@@ -219,18 +219,35 @@ def main():
     heads_dev = [[x.to(dev, non_blocking=True) for x in lv] for lv in heads_host]
     torch.cuda.synchronize()
 
+    # N > 1: the NMS kernel writes into a packed per-rank buffer that ONE asynchronous gather moves to
+    # rank 0; two buffers alternate so the gather of step k overlaps the kernels of step k+1.
+    gatherers = [DetectionGatherer(len(NCS), B_PER_GPU, NMS_KW["max_det"], dev, dst=0) for _ in range(2)] if world > 1 else None
+    step_no = [0]
+
     def step(record=None):
         if record is not None:
             record[0].record()
         ys = ops.decode_heads(heads_dev, STRIDES)
         if record is not None:
             record[1].record()
-        dets, counts = ops.nms_batched(ys, **NMS_KW)
-        if record is not None:
-            record[2].record()
         if world > 1:
-            dets, counts = gather_detections(dets, counts, dst=0)
+            g = gatherers[step_no[0] & 1]
+            step_no[0] += 1
+            g.wait()  # the gather issued from this buffer two steps ago
+            dets, counts = ops.nms_batched(ys, out=g.out, **NMS_KW)
+            if record is not None:
+                record[2].record()
+            g.launch()
+        else:
+            dets, counts = ops.nms_batched(ys, **NMS_KW)
+            if record is not None:
+                record[2].record()
         return dets, counts
+
+    def drain():
+        if world > 1:
+            for g in gatherers:
+                g.wait()
 
     def barrier():
         if world > 1:
@@ -239,6 +256,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,6 +265,7 @@ def main():
         t_start.record()
         for k in range(args.steps):
             step(evs[k])
+        drain()  # every batch's detections have reached rank 0
         t_end.record()
         barrier()
     elapsed_ms = t_start.elapsed_time(t_end)

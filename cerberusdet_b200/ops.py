@@ -108,6 +108,7 @@ def _nms_impl(
     max_nms: int,
     max_wh: float,
     smax: Sequence[torch.Tensor],
+    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     T = len(preds)
@@ -122,8 +123,15 @@ def _nms_impl(
         ncs.append(int(p.shape[1]) - 4)
         ps.append(p.contiguous())
     dev = first.device
-    dets = torch.empty((T, B, max_det, 6), dtype=torch.float32, device=dev)  # the kernel writes every row
-    counts = torch.empty((T, B), dtype=torch.int32, device=dev)
+    if out is not None:
+        dets, counts = out
+        if (tuple(dets.shape) != (T, B, max_det, 6) or dets.dtype != torch.float32 or not dets.is_contiguous()
+                or tuple(counts.shape) != (T, B) or counts.dtype != torch.int32 or not counts.is_contiguous()
+                or dets.device != dev or counts.device != dev):
+            raise ValueError("out= must be contiguous (dets[T,B,max_det,6] float32, counts[T,B] int32) on the input device")
+    else:
+        dets = torch.empty((T, B, max_det, 6), dtype=torch.float32, device=dev)  # the kernel writes every row
+        counts = torch.empty((T, B), dtype=torch.int32, device=dev)
     ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     cls_arr = _lib.int_array(list(classes)) if classes is not None else None
@@ -230,10 +238,12 @@ def nms_batched(
     max_nms: int = MAX_NMS,
     max_wh: float = MAX_WH,
     use_summary: bool = True,
+    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """All task heads, all images, one launch.  Returns padded ``dets[T,B,max_det,6]`` and
     ``counts[T,B]`` (device tensors; no host sync).  Predictions that came out of ``decode_heads``
-    unmodified bring their score summary along, which spares the kernel the full score scans."""
+    unmodified bring their score summary along, which spares the kernel the full score scans.
+    ``out=(dets, counts)`` writes into caller-provided buffers (e.g. ``shard.DetectionGatherer``'s)."""
     # reference asserts (utils/general.py:399-400) -- same exception type and wording
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
@@ -245,4 +255,4 @@ def nms_batched(
             smax = found
     return _nms_impl(preds, float(conf_thres), float(iou_thres),
                   None if classes is None else [int(c) for c in classes],
-                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)
+                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax, out)

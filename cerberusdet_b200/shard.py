@@ -60,3 +60,53 @@ def gather_detections(
         return None, None
     return (torch.cat([d[:, :n] for d, n in zip(d_list, sizes)], 1),
             torch.cat([c[:, :n] for c, n in zip(c_list, sizes)], 1))
+
+
+class DetectionGatherer:
+    """Persistent buffers for the per-batch gather: the NMS kernel writes ``dets`` and ``counts`` straight
+    into one packed buffer per rank, so a batch needs ONE collective (``dist.gather`` of
+    ``T*B*(max_det*6+1)`` 32-bit words) and no per-step allocation.  ``launch()`` is asynchronous; the
+    gathered tensors on ``dst`` are valid after ``wait()``.  Equal shards only (pad the batch otherwise,
+    or use ``gather_detections``)."""
+
+    def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
+        self.T, self.b_loc, self.max_det, self.dst, self.group = T, b_loc, max_det, dst, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n_d, n_c = T * b_loc * max_det * 6, T * b_loc
+        self.local = torch.empty(n_d + n_c, dtype=torch.float32, device=device)
+        self.dets = self.local[:n_d].view(T, b_loc, max_det, 6)
+        self.counts = self.local[n_d:].view(torch.int32).view(T, b_loc)
+        self.all = None
+        if self.rank == dst and self.world > 1:
+            self.all = torch.empty((self.world, n_d + n_c), dtype=torch.float32, device=device)
+            self._views = [self.all[r] for r in range(self.world)]
+        self._n_d = n_d
+        self._work = None
+
+    @property
+    def out(self):
+        return self.dets, self.counts
+
+    def launch(self):
+        if self.world > 1:
+            self._work = dist.gather(self.local, self._views if self.rank == self.dst else None, dst=self.dst,
+                                     group=self.group, async_op=True)
+        return self._work
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+
+    def result(self) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """``(dets[T, world*B_loc, max_det, 6], counts[T, world*B_loc])`` on ``dst`` in global image order."""
+        self.wait()
+        if self.world == 1:
+            return self.dets, self.counts
+        if self.rank != self.dst:
+            return None, None
+        d = self.all[:, : self._n_d].view(self.world, self.T, self.b_loc, self.max_det, 6)
+        c = self.all[:, self._n_d :].view(torch.int32).view(self.world, self.T, self.b_loc)
+        return (d.permute(1, 0, 2, 3, 4).reshape(self.T, self.world * self.b_loc, self.max_det, 6),
+                c.permute(1, 0, 2).reshape(self.T, self.world * self.b_loc))

@@ -84,7 +84,7 @@ def greedy_nms_c(boxes: torch.Tensor, iou_thres: float) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- decode
-def anchor_grid(level_hw: Sequence[Sequence[int]], strides: Sequence[float], dtype):
+def anchor_grid(level_hw: Sequence[Sequence[int]], strides: Sequence[float], dtype, device="cpu"):
     """``make_anchors`` (utils/tal.py:181-193) + the transpose at models/yolo.py:94.
 
     Anchor k of a level with width w sits at (k % w + 0.5, k // w + 0.5) in grid
@@ -93,11 +93,11 @@ def anchor_grid(level_hw: Sequence[Sequence[int]], strides: Sequence[float], dty
     """
     pts, st = [], []
     for (h, w), s in zip(level_hw, strides):
-        xs = torch.arange(w, dtype=dtype) + 0.5
-        ys = torch.arange(h, dtype=dtype) + 0.5
+        xs = torch.arange(w, dtype=dtype, device=device) + 0.5
+        ys = torch.arange(h, dtype=dtype, device=device) + 0.5
         gy, gx = torch.meshgrid(ys, xs, indexing="ij")
         pts.append(torch.stack((gx, gy), -1).reshape(-1, 2))
-        st.append(torch.full((h * w, 1), float(s), dtype=dtype))
+        st.append(torch.full((h * w, 1), float(s), dtype=dtype, device=device))
     return torch.cat(pts).transpose(0, 1), torch.cat(st).transpose(0, 1)
 
 
@@ -111,7 +111,7 @@ def dfl_expectation(box_logits: torch.Tensor) -> torch.Tensor:
     """
     b, _, a = box_logits.shape
     probs = box_logits.view(b, 4, REG_MAX, a).transpose(2, 1).softmax(1)  # [b,16,4,a]
-    w = torch.arange(REG_MAX, dtype=torch.float).view(1, REG_MAX, 1, 1).to(box_logits.dtype)
+    w = torch.arange(REG_MAX, dtype=torch.float).view(1, REG_MAX, 1, 1).to(box_logits)
     return F.conv2d(probs, w).view(b, 4, a)
 
 
@@ -133,7 +133,7 @@ def decode_port(levels: Sequence[torch.Tensor], nc: int, strides: Sequence[float
     bsz = levels[0].shape[0]
     no = 4 * REG_MAX + nc
     dtype = levels[0].dtype
-    anchors, stride_row = anchor_grid([t.shape[2:] for t in levels], strides, dtype)
+    anchors, stride_row = anchor_grid([t.shape[2:] for t in levels], strides, dtype, levels[0].device)
     flat = torch.cat([t.reshape(bsz, no, -1) for t in levels], 2)  # models/yolo.py:97
     box_logits, cls_logits = flat[:, : 4 * REG_MAX], flat[:, 4 * REG_MAX :]
     dbox = ltrb_to_xywh(dfl_expectation(box_logits), anchors.unsqueeze(0)) * stride_row  # yolo.py:98

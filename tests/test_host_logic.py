@@ -169,3 +169,40 @@ def test_patch_install_rebinds_and_restores():
     finally:
         patch.uninstall()
     assert ref.yolo.Detect.forward is orig_fwd and ref.general.non_max_suppression is orig_nms
+
+
+_WORKER2 = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from cerberusdet_b200.shard import DetectionGatherer
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+T, BL, MD = 3, 4, 5
+g = torch.Generator().manual_seed(1)
+full_d = torch.rand(T, world * BL, MD, 6, generator=g); full_c = torch.randint(0, MD + 1, (T, world * BL), generator=g, dtype=torch.int32)
+gat = DetectionGatherer(T, BL, MD, "cpu", dst=0)
+for rep in range(3):                                   # buffers are reused across batches
+    d, c = gat.out
+    d.copy_(full_d[:, rank * BL:(rank + 1) * BL] + rep); c.copy_(full_c[:, rank * BL:(rank + 1) * BL])
+    gat.launch()
+    D, C = gat.result()
+    if rank == 0:
+        assert torch.equal(D, full_d + rep) and torch.equal(C, full_c)
+    else:
+        assert D is None and C is None
+if rank == 0:
+    print("GATHERER_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_detection_gatherer_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker2.py"
+    script.write_text(_WORKER2.format(root=ROOT, port=29612))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHERER_OK" in outs[0]
