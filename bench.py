@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the two kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -254,6 +255,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    for _ in range(max(args.warmup // 2, 3)):
+        step()
+    drain()
+    barrier()
+
+    # Launch-bound inner loop -> CUDA graphs: graph A = decode_kernel, graph B = nms_kernel (+ the gather to
+    # rank 0 for N > 1).  Two graphs so the decode kernel can still be bracketed by events in the timed region.
+    mode = "eager"
+    if not args.no_graphs:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g_dec = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_dec, stream=side):
+                    ys_static = ops.decode_heads(heads_dev, STRIDES)
+                # one NMS graph per output buffer (N > 1 alternates two gather buffers); the NCCL gather itself
+                # stays outside the graphs and is issued asynchronously after the replay
+                g_nms, outs_static = [], []
+                for i in range(2 if world > 1 else 1):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        o = ops.nms_batched(ys_static, out=gatherers[i].out, **NMS_KW) if world > 1 else ops.nms_batched(ys_static, **NMS_KW)
+                    g_nms.append(g)
+                    outs_static.append(o)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+
+            def step(record=None):  # noqa: F811
+                i = step_no[0] & 1 if world > 1 else 0
+                step_no[0] += 1
+                if record is not None:
+                    record[0].record()
+                g_dec.replay()
+                if record is not None:
+                    record[1].record()
+                if world > 1:
+                    gatherers[i].wait()  # the gather issued from this buffer two steps ago
+                g_nms[i].replay()
+                if record is not None:
+                    record[2].record()
+                if world > 1:
+                    gatherers[i].launch()
+                return outs_static[i]
+
+            mode = "cuda_graphs"
+        except Exception as exc:  # pragma: no cover - depends on the driver/NCCL build
+            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
     drain()
@@ -317,6 +367,7 @@ def main():
             "e2e": {"value": B_PER_GPU * world * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": 2 * args.steps,  # decode_kernel + nms_kernel per step, nothing else
+            "launch_mode": mode,
             "clocks": clk.summary(),
         }
         if not args.no_cpu_baseline:
