@@ -83,7 +83,15 @@ template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x
 // streaming 128-bit / 64-bit / scalar accesses (read once, write once: keep them out of L1)
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
     uint4 r;
+#if defined(CERB_LD_L2_256)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif defined(CERB_LD_L2_128)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif defined(CERB_LD_PLAIN)
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;

@@ -17,6 +17,7 @@ struct DecodeParams {
     int row_start[CERB_MAX_TASKS * CERB_MAX_LEVELS + 1];        // first block of each (task, level) row
     int row_blocks_per_part[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // ceil(B * nvecp / threads)
     void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V]: max of every 16-byte score vector
+    int interleave_parts;        // block order of the parts inside a row (see decode.cu)
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
 // persistent TMA-pipelined variant; needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one

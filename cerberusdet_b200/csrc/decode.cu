@@ -68,10 +68,12 @@ template <typename T, int VEC> __device__ __forceinline__ T pack_max(const Pack<
 // Rounding points follow the reference for half tensors: probabilities are rounded to
 // half (softmax output), the 1x1 conv accumulates in fp32 and rounds once.
 template <typename T, int VEC>
-__device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw, float (&d)[VEC]) {
-    Pack<T, VEC> v[CERB_REG_MAX];
+__device__ __forceinline__ void dfl_load(const T* __restrict__ side_base, int hw, Pack<T, VEC> (&v)[CERB_REG_MAX]) {
 #pragma unroll
     for (int k = 0; k < CERB_REG_MAX; ++k) v[k] = load_pack<T, VEC>(side_base + (size_t)k * hw);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void dfl_reduce(const Pack<T, VEC> (&v)[CERB_REG_MAX], float (&d)[VEC]) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         float x[CERB_REG_MAX];
@@ -79,6 +81,12 @@ __device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw
         for (int k = 0; k < CERB_REG_MAX; ++k) x[k] = to_f32<T>(v[k].e[i]);
         d[i] = dfl_expectation<T>(x);
     }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void dfl_side(const T* __restrict__ side_base, int hw, float (&d)[VEC]) {
+    Pack<T, VEC> v[CERB_REG_MAX];
+    dfl_load<T, VEC>(side_base, hw, v);
+    dfl_reduce<T, VEC>(v, d);
 }
 
 template <typename T, int VEC>
@@ -96,8 +104,18 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
     const int task = row / P.L, level = row - task * P.L;
     const int in_row = blockIdx.x - P.row_start[row];
     const int bpp = P.row_blocks_per_part[row];
-    const int part = in_row / bpp;
-    const int vblk = in_row - part * bpp;
+    // Block order of the parts.  Contiguous ([all DFL l,r blocks][all t,b][classes]) is faster for fp16
+    // (81.5 vs 87.7 us); interleaved (DFL and class blocks share every SM at all times) is faster for fp32,
+    // which is HBM-bound (113.7 vs 118.8 us) -- profiles/r01_decode.md.
+    int part, vblk;
+    if (P.interleave_parts) {
+        const int nparts = 2 + (P.nc[task] + CLS_CHUNK - 1) / CLS_CHUNK;
+        vblk = in_row / nparts;
+        part = in_row - vblk * nparts;
+    } else {
+        part = in_row / bpp;
+        vblk = in_row - part * bpp;
+    }
 
     const int hw = P.hw[level];
     const int nvec = hw / VEC;
@@ -125,8 +143,18 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)k * hw));
         }
 #endif
+#ifdef DEC_DOUBLE_BUFFER  // both sides' loads in flight before the first reduction (more registers, fewer warps)
+        {
+            Pack<T, VEC> va[CERB_REG_MAX], vb[CERB_REG_MAX];
+            dfl_load<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, va);
+            dfl_load<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, vb);
+            dfl_reduce<T, VEC>(va, dlo);
+            dfl_reduce<T, VEC>(vb, dhi);
+        }
+#else
         dfl_side<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, dlo);
         dfl_side<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, dhi);
+#endif
         const int W = P.w[level];
         const float st = P.stride[level];
         Pack<T, VEC> oc, os;
