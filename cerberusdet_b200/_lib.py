@@ -21,6 +21,7 @@ EXPORTS = (
     "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
+    "cerb_cross_task",
     "cerb_debug_set_chunking",
     "cerb_debug_set_hist_sample",
 )
@@ -57,6 +58,8 @@ def load() -> ctypes.CDLL:
     lib.cerb_nms_workspace_bytes.argtypes = [i, i, i]
     lib.cerb_nms.restype = i
     lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp]
+    lib.cerb_cross_task.restype = i
+    lib.cerb_cross_task.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp]
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
     lib.cerb_debug_set_hist_sample.restype = i

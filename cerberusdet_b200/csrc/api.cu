@@ -227,3 +227,25 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
     }
     return 0;
 }
+
+extern "C" int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
+                               double iou_thres, const float* scale, float* out, int* out_counts, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_cross_task: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
+    REQUIRE(B >= 0 && max_det >= 0, "cerb_cross_task: negative size");
+    REQUIRE((long)T * max_det <= 1024, "cerb_cross_task: T*max_det=%ld exceeds 1024 rows per image", (long)T * max_det);
+    if (B == 0) return 0;
+    REQUIRE(counts && class_offset && out_counts && (dets || max_det == 0) && (out || max_det == 0), "cerb_cross_task: null argument");
+    CrossTaskParams P;
+    memset(&P, 0, sizeof(P));
+    P.dets = dets; P.counts = counts; P.T = T; P.B = B; P.max_det = max_det;
+    for (int t = 0; t < T; ++t) P.class_offset[t] = class_offset[t];
+    P.iou_thr = (float)iou_thres;
+    P.scale = scale; P.out = out; P.out_counts = out_counts;
+    cudaError_t e = cerb_launch_cross_task(P, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_cross_task: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}

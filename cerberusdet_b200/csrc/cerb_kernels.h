@@ -49,3 +49,16 @@ struct NmsParams {
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);
+
+// ------------------------------------------------------------------ cross-task merge
+struct CrossTaskParams {
+    const float* dets;       // [T, B, max_det, 6] per-task NMS rows (local class ids)
+    const int* counts;       // [T, B]
+    int T, B, max_det;
+    int class_offset[CERB_MAX_TASKS];  // local -> global class id
+    float iou_thr;           // (float)iou_thres_between_tasks: compared like the reference's fp32 matrix > python float
+    const float* scale;      // optional [B, 5]: gain, pad_x, pad_y, orig_w, orig_h (scale_boxes + round), else null
+    float* out;              // [B, T*max_det, 6] merged rows, global class ids
+    int* out_counts;         // [B]
+};
+cudaError_t cerb_launch_cross_task(const CrossTaskParams& P, cudaStream_t stream);

@@ -16,7 +16,7 @@ import torch
 
 from . import cross_task
 from .detect import _RAW_FLAG
-from .ops import decode_heads, nms_batched
+from .ops import cross_task_merge, decode_heads, nms_batched
 
 
 @contextlib.contextmanager
@@ -107,19 +107,39 @@ class CerberusDetInference:
         if any(p is None for p in preds):  # raw mode was honoured: decode all heads in one launch
             levels = [all_out[t][1] for t in tasks]
             preds = decode_heads(levels, self._head_strides(len(levels[0])))
-        # 2. one NMS launch over all (task, image) segments; one D2H copy
+        # 2. one NMS launch over all (task, image) segments
         dets, counts = nms_batched(preds, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det)
-        dets_h, counts_h = dets.cpu(), counts.cpu()
-
-        results = []
         bsz = tensor.shape[0]
-        for i in range(bsz):
-            per_task = {t: dets_h[k, i, : int(counts_h[k, i])] for k, t in enumerate(tasks)}
-            det = cross_task.combine_tasks(per_task, self.categories_inds_map)
-            det = cross_task.suppress_between_tasks(det, self.categories_inds_map, between)
-            if len(det) > 0 and original_shape is not None:
-                shp = original_shape[i] if isinstance(original_shape, list) else original_shape
-                det[:, :4] = cross_task.rescale_boxes(tensor.shape[2:], det[:, :4], shp).round()
+        shapes = None
+        if original_shape is not None:
+            shapes = original_shape if isinstance(original_shape, list) else [original_shape] * bsz
+        results = []
+        if len(tasks) * max_det <= 1024:
+            # 3. cross-task merge + rescale on the GPU (one launch, one CTA per image), then ONE D2H copy
+            offsets = [min(self.categories_inds_map[t].values()) if self.categories_inds_map[t] else 0 for t in tasks]
+            scale = None
+            if shapes is not None:
+                net_h, net_w = int(tensor.shape[2]), int(tensor.shape[3])
+                rows = []
+                for (oh, ow) in shapes:
+                    gain = min(net_h / oh, net_w / ow)  # utils/general.py:330-331
+                    rows.append([gain, (net_w - ow * gain) / 2, (net_h - oh * gain) / 2, float(ow), float(oh)])
+                scale = torch.tensor(rows, dtype=torch.float64).to(torch.float32)
+            merged, mcounts = cross_task_merge(dets, counts, offsets, between, scale)
+            merged_h, mcounts_h = merged.cpu(), mcounts.cpu()
+            per_image = [merged_h[i, : int(mcounts_h[i])] for i in range(bsz)]
+        else:
+            # too many rows per image for the shared-memory bitmask: host tail, as in the reference
+            dets_h, counts_h = dets.cpu(), counts.cpu()
+            per_image = []
+            for i in range(bsz):
+                per_task = {t: dets_h[k, i, : int(counts_h[k, i])] for k, t in enumerate(tasks)}
+                det = cross_task.combine_tasks(per_task, self.categories_inds_map)
+                det = cross_task.suppress_between_tasks(det, self.categories_inds_map, between)
+                if len(det) > 0 and shapes is not None:
+                    det[:, :4] = cross_task.rescale_boxes(tensor.shape[2:], det[:, :4], shapes[i]).round()
+                per_image.append(det)
+        for det in per_image:
             image_results = []
             for *xyxy, conf, cls in det.tolist():
                 c = int(cls)

@@ -256,3 +256,29 @@ def nms_batched(
     return _nms_impl(preds, float(conf_thres), float(iou_thres),
                   None if classes is None else [int(c) for c in classes],
                   bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax, out)
+
+
+def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Sequence[int], iou_thres: float,
+                     scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Batched GPU form of the reference's per-image tail after NMS (cerberusdet_inference.py:140-155):
+    combine the tasks' rows with global class ids, ``nms_between_tasks``, optional ``scale_boxes().round()``.
+    ``scale`` is a device ``[B, 5]`` float tensor (gain, pad_x, pad_y, orig_w, orig_h) or None.
+    Returns ``merged[B, T*max_det, 6]`` and ``counts[B]`` (device)."""
+    lib = _lib.load()
+    _require_cuda(dets, "dets")
+    T, B, max_det, _ = dets.shape
+    if T * max_det > 1024:
+        raise ValueError("cross_task_merge supports T*max_det <= 1024 rows per image")
+    dets, counts = dets.contiguous(), counts.contiguous()
+    out = torch.empty((B, T * max_det, 6), dtype=torch.float32, device=dets.device)
+    out_counts = torch.empty((B,), dtype=torch.int32, device=dets.device)
+    if scale is not None:
+        scale = scale.to(device=dets.device, dtype=torch.float32).contiguous()
+        if tuple(scale.shape) != (B, 5):
+            raise ValueError("scale must be [B, 5]")
+    with torch.cuda.device(dets.device):
+        rc = lib.cerb_cross_task(dets.data_ptr(), counts.data_ptr(), T, B, max_det, _lib.int_array([int(o) for o in class_offsets]),
+                                 float(iou_thres), scale.data_ptr() if scale is not None else None, out.data_ptr(),
+                                 out_counts.data_ptr(), _stream_ptr(dets.device))
+    _lib.check(rc)
+    return out, out_counts

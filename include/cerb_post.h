@@ -101,6 +101,23 @@ int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dt
              size_t workspace_bytes, void* stream);
 
 /*
+ * Cross-task merge of the per-task NMS results for a whole batch in one launch (one CTA per image).
+ * Replaces the per-image host loop of CerberusDetInference.predict
+ * (cerberusdet/cerberusdet_inference.py:140-155): _combine_output (:72-83, local -> global class ids),
+ * nms_between_tasks (cerberusdet/utils/general.py:484-554, with box_iou of utils/metrics.py:415-433) and the
+ * optional scale_boxes(...).round() (utils/general.py:313-357).
+ *
+ *   dets, counts   the outputs of cerb_nms: [T, B, max_det, 6], [T, B]
+ *   class_offset   host [T]: global id = local id + class_offset[t]
+ *   scale          optional device [B, 5] = (gain, pad_x, pad_y, orig_w, orig_h) per image, or NULL
+ *   out            [B, T*max_det, 6] merged rows (x1, y1, x2, y2, conf, global cls), task order kept;
+ *   out_counts     [B]
+ * Needs T*max_det <= 1024 (the per-image IoU bitmask lives in shared memory).
+ */
+int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
+                    double iou_thres, const float* scale, float* out, int* out_counts, void* stream);
+
+/*
  * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy
  * top-k so small inputs exercise the multi-chunk and radix-refinement paths.
  * (0, 0) restores the defaults.  Results never depend on these values.

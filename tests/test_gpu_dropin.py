@@ -135,3 +135,78 @@ def test_inference_mirror_matches_oracle_pipeline(patched, half):
             assert g["label_name"] == eng.all_class_names[g["label"]]
             assert g["task"] == ("voc" if g["label"] < 20 else "animals")
     assert sum(len(r) for r in got) > 0
+
+
+def _random_task_dets(gen, T, B, max_det, clustered, ties):
+    """Padded per-task NMS-like outputs with overlapping boxes across tasks (and exact score ties)."""
+    dets = torch.zeros(T, B, max_det, 6)
+    counts = torch.zeros(T, B, dtype=torch.int32)
+    for b in range(B):
+        k = 5
+        centres = torch.rand(k, 2, generator=gen) * 400 + 100
+        for t in range(T):
+            n = int(torch.randint(0, max_det + 1, (1,), generator=gen))
+            if b == 1 and t == 0:
+                n = 0  # an empty task
+            pick = torch.randint(0, k, (n,), generator=gen)
+            c = centres[pick] + torch.randn(n, 2, generator=gen) * (3 if clustered else 90)
+            wh = 50 + torch.rand(n, 2, generator=gen) * 30
+            sc = torch.rand(n, generator=gen)
+            if ties:
+                sc = (sc * 8).round() / 8  # many exactly equal scores, also across tasks
+            sc = sc.sort(descending=True).values
+            dets[t, b, :n] = torch.cat((c - wh / 2, c + wh / 2, sc[:, None], torch.randint(0, 12, (n, 1), generator=gen).float()), 1)
+            counts[t, b] = n
+    return dets, counts
+
+
+@pytest.mark.parametrize("clustered,ties", [(True, False), (True, True), (False, False)])
+@pytest.mark.parametrize("thr", [0.8, 0.5, 0.05])
+@pytest.mark.parametrize("with_scale", [False, True])
+def test_cross_task_merge_matches_host_tail(clustered, ties, thr, with_scale):
+    """GPU cross-task merge == cross_task.py (itself pinned to the reference's nms_between_tasks / scale_boxes
+    by tests/test_host_logic.py), bit for bit, including equal-score ties and the all-deleted rule."""
+    from cerberusdet_b200 import cross_task as ct
+    from cerberusdet_b200.ops import cross_task_merge
+
+    gen = torch.Generator().manual_seed(int(clustered) * 7 + int(ties) * 3 + int(thr * 100))
+    T, B, md = 3, 5, 40
+    dets, counts = _random_task_dets(gen, T, B, md, clustered, ties)
+    names = {"a": ["x"] * 12, "b": ["y"] * 12, "c": ["z"] * 12}
+    maps, _ = ct.category_maps(names)
+    offsets = [0, 12, 24]
+    shapes = [(480, 640), (1080, 1920), (333, 500), (640, 640), (100, 900)]
+    scale = None
+    if with_scale:
+        rows = []
+        for (oh, ow) in shapes:
+            gain = min(640 / oh, 640 / ow)
+            rows.append([gain, (640 - ow * gain) / 2, (640 - oh * gain) / 2, float(ow), float(oh)])
+        scale = torch.tensor(rows, dtype=torch.float64).to(torch.float32)
+    merged, mc = cross_task_merge(dets.cuda(), counts.cuda(), offsets, thr, scale)
+    merged, mc = merged.cpu(), mc.cpu()
+    for b in range(B):
+        per_task = {t: dets[k, b, : int(counts[k, b])] for k, t in enumerate(names)}
+        want = ct.combine_tasks(per_task, maps)
+        want = ct.suppress_between_tasks(want, maps, thr)
+        if with_scale and len(want):
+            want[:, :4] = ct.rescale_boxes((640, 640), want[:, :4], shapes[b]).round()
+        got = merged[b, : int(mc[b])]
+        assert got.shape == want.shape, (b, got.shape, want.shape)
+        assert torch.equal(got, want), b
+
+
+def test_cross_task_merge_everything_deleted_keeps_everything():
+    """Two tasks with one identical box each and equal scores: the column wins the tie and the row is deleted;
+    with mutual total deletion the reference returns the input unchanged (general.py:551-552)."""
+    from cerberusdet_b200 import cross_task as ct
+    from cerberusdet_b200.ops import cross_task_merge
+
+    dets = torch.zeros(2, 1, 4, 6)
+    counts = torch.tensor([[1], [1]], dtype=torch.int32)
+    dets[0, 0, 0] = torch.tensor([10, 10, 50, 50, 0.5, 1.0])
+    dets[1, 0, 0] = torch.tensor([10, 10, 50, 50, 0.5, 2.0])
+    maps, _ = ct.category_maps({"a": ["x"] * 3, "b": ["y"] * 3})
+    merged, mc = cross_task_merge(dets.cuda(), counts.cuda(), [0, 3], 0.5)
+    want = ct.suppress_between_tasks(ct.combine_tasks({"a": dets[0, 0, :1], "b": dets[1, 0, :1]}, maps), maps, 0.5)
+    assert int(mc[0]) == want.shape[0] and torch.equal(merged[0, : int(mc[0])].cpu(), want)
