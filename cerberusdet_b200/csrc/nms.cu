@@ -54,9 +54,19 @@ extern "C" int cerb_debug_read_profile(unsigned long long* out16, int reset) {
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_nms_prof, z, sizeof(z)); }
     return 0;
 }
+__device__ long long g_prof_t;
+#define PROFX(slot)                                                       \
+    do {                                                                  \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                        \
+            const long long now = clock64();                              \
+            g_nms_prof[slot] += (unsigned long long)(now - g_prof_t);     \
+            g_prof_t = now;                                               \
+        }                                                                 \
+    } while (0)
 #else
 #define PROF_DECL
 #define PROF(slot) do {} while (0)
+#define PROFX(slot) do {} while (0)
 #endif
 
 struct __align__(16) NmsSmem {
@@ -123,6 +133,27 @@ __device__ __forceinline__ void warp_hist_add(unsigned* hist, unsigned bin) {
     const unsigned active = __activemask();
     const unsigned peers = __match_any_sync(active, bin);
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
+// Slot reservation without a returning atomic per item: a shared-memory atomicAdd that returns a value costs ~13
+// cycles and same-address ones serialise across the whole CTA (1.2 k list pushes = 15 k cycles, measured), so every
+// lane first counts its items, the warp prefix-sums the counts and ONE lane reserves the warp's total.  Must be
+// called by all 32 lanes; returns this lane's first slot.
+__device__ __forceinline__ unsigned warp_reserve(unsigned* counter, unsigned n) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned base = 0;
+    if (total) {
+        if (lane == 31u) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    return base + inc - n;
 }
 
 template <typename T> struct ScoreVec {
@@ -306,7 +337,10 @@ template <typename T, bool MULTI, bool WITH_SCORES, typename F>
 __device__ __forceinline__ bool for_each_candidate_summary(const T* __restrict__ img, const T* __restrict__ smax,
                                                            int nc, int A, float thr, const NmsParams& P, F f,
                                                            unsigned sb_lo, unsigned sb_hi, unsigned* hits,
-                                                           unsigned* nhits) {
+                                                           unsigned* nhits, u64 lo = 0, u64 hi = 0, u64* keys = nullptr,
+                                                           unsigned* counter = nullptr) {
+    // WITH_SCORES: the keys in [lo, hi) are appended to keys[] / *counter (slots reserved per warp, see
+    // warp_reserve).  !WITH_SCORES: f(max_bits, 0, 0) per summary entry in range (the estimating histogram).
     constexpr int V = ScoreVec<T>::V;
     const T* __restrict__ sc = img + (size_t)4 * A;
     const unsigned NV = (unsigned)A / V;          // score vectors per class row
@@ -327,8 +361,9 @@ __device__ __forceinline__ bool for_each_candidate_summary(const T* __restrict__
         if (threadIdx.x == 0) *nhits = 0;
         __syncthreads();
     }
-    // ---- pass 1: the summary
-    for (unsigned q0 = threadIdx.x; q0 < nsv; q0 += NMS_THREADS * SCAN_UNROLL) {
+    // ---- pass 1: the summary (block-uniform trip count: warp_reserve needs whole warps)
+    for (unsigned qb = 0; qb < nsv; qb += NMS_THREADS * SCAN_UNROLL) {
+        const unsigned q0 = qb + threadIdx.x;
         ScoreVec<T> m[SCAN_UNROLL];
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; ++u) {
@@ -339,10 +374,13 @@ __device__ __forceinline__ bool for_each_candidate_summary(const T* __restrict__
                 m[u].raw = __ldg(reinterpret_cast<const uint4*>(smax + (size_t)c * SNV + j0));
             }
         }
+        unsigned h[SCAN_UNROLL], ebase[SCAN_UNROLL], cnt = 0;
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; ++u) {
+            h[u] = 0;
+            ebase[u] = 0;
             const unsigned q = q0 + u * NMS_THREADS;
-            if (q >= nsv) break;
+            if (q >= nsv) continue;
             const unsigned c = MULTI ? q / SV : 0u;
             const unsigned j0 = (MULTI ? q - c * SV : q) * V;  // first entry of this summary vector in its row
             if (MULTI) {
@@ -356,93 +394,147 @@ __device__ __forceinline__ bool for_each_candidate_summary(const T* __restrict__
                         if (to_f32<T>(o.e[k]) > to_f32<T>(m[u].e[k])) m[u].e[k] = o.e[k];
                 }
             }
-            const unsigned h = range_hits<T>(m[u], sb_lo, 0x7F800000u, rb_any);
-            if (!h) continue;
+            unsigned hm = range_hits<T>(m[u], sb_lo, 0x7F800000u, rb_any);
+            if (j0 + V > NV) hm &= (1u << (NV - j0)) - 1u;  // row padding
+            h[u] = hm;
+            ebase[u] = c * NV + j0;
+            cnt += __popc(hm);
+        }
+        if (WITH_SCORES) {
+            unsigned pos = warp_reserve(nhits, cnt);
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                if (!((h >> k) & 1u) || j0 + k >= NV) continue;
-                if (WITH_SCORES) {
-                    const unsigned p = atomicAdd(nhits, 1u);
-                    if (p < NMS_BINS) hits[p] = c * NV + j0 + k;
-                } else {
-                    const unsigned sbm = make_sbits(to_f32<T>(m[u].e[k]));
-                    if (sbm <= sb_hi) f(sbm, 0, 0);
-                }
-            }
+            for (int u = 0; u < SCAN_UNROLL; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if ((h[u] >> k) & 1u) {
+                        if (pos < NMS_BINS) hits[pos] = ebase[u] + k;
+                        ++pos;
+                    }
+        } else {
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if ((h[u] >> k) & 1u) {
+                        const unsigned sbm = make_sbits(to_f32<T>(m[u].e[k]));
+                        if (sbm <= sb_hi) f(sbm, 0, 0);
+                    }
         }
     }
     if (!WITH_SCORES) return true;
+    PROFX(12);  // collect: pass 1 (this thread)
     __syncthreads();
     const unsigned nh = *nhits;
     __syncthreads();
+    PROFX(13);  // collect: wait for the block
     if (nh > NMS_BINS) return false;  // dense: not worth (and not possible) to list
     // ---- pass 2: the listed score vectors
     if (MULTI) {
-        for (unsigned i0 = threadIdx.x; i0 < nh; i0 += NMS_THREADS * SCAN_UNROLL) {
+        for (unsigned ib = 0; ib < nh; ib += NMS_THREADS * SCAN_UNROLL) {
+            const unsigned i0 = ib + threadIdx.x;
             ScoreVec<T> v[SCAN_UNROLL];
             unsigned e_[SCAN_UNROLL];
 #pragma unroll
             for (int u = 0; u < SCAN_UNROLL; ++u) {
                 const unsigned i = i0 + u * NMS_THREADS;
+                e_[u] = 0;
                 if (i < nh) {
                     e_[u] = hits[i];
                     const unsigned c = e_[u] / NV;
                     v[u].raw = __ldg(reinterpret_cast<const uint4*>(sc + (size_t)c * A + (size_t)(e_[u] - c * NV) * V));
                 }
             }
+            unsigned hv[SCAN_UNROLL], cnt = 0;
 #pragma unroll
             for (int u = 0; u < SCAN_UNROLL; ++u) {
+                hv[u] = 0;
                 const unsigned i = i0 + u * NMS_THREADS;
-                if (i >= nh) break;
-                const unsigned hv = range_hits<T>(v[u], sb_lo, sb_hi, rb);
-                if (!hv) continue;
+                if (i >= nh) continue;
+                unsigned hm = range_hits<T>(v[u], sb_lo, sb_hi, rb);
+                if (hm && ((unsigned)lo | (unsigned)hi)) {  // bounds not digit-aligned (refinement): full key compare
+                    const unsigned c = e_[u] / NV, a_s = (e_[u] - c * NV) * V;
+#pragma unroll
+                    for (int k = 0; k < V; ++k)
+                        if ((hm >> k) & 1u) {
+                            const u64 key = make_key(make_sbits(to_f32<T>(v[u].e[k])), (a_s + k) * (unsigned)nc + c);
+                            if (!(key >= lo && key < hi)) hm &= ~(1u << k);
+                        }
+                }
+                hv[u] = hm;
+                cnt += __popc(hm);
+            }
+            unsigned pos = warp_reserve(counter, cnt);
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u) {
+                if (!hv[u]) continue;
                 const unsigned c = e_[u] / NV, a_s = (e_[u] - c * NV) * V;
 #pragma unroll
                 for (int k = 0; k < V; ++k)
-                    if ((hv >> k) & 1u) f(make_sbits(to_f32<T>(v[u].e[k])), (int)(a_s + k), (int)c);
+                    if ((hv[u] >> k) & 1u) {
+                        if (pos < NMS_CAP) keys[pos] = make_key(make_sbits(to_f32<T>(v[u].e[k])), (a_s + k) * (unsigned)nc + c);
+                        ++pos;
+                    }
             }
         }
     } else {
-        for (unsigned i = threadIdx.x; i < nh; i += NMS_THREADS) {
-            const unsigned a_s = hits[i] * V;
-            const uint4* __restrict__ col = reinterpret_cast<const uint4*>(sc + a_s);
-            const size_t rowv = (size_t)A / V;
-            float best[V];
-            int bc[V];
+        for (unsigned ib = 0; ib < nh; ib += NMS_THREADS) {
+            const unsigned i = ib + threadIdx.x;
+            u64 mykeys[V];
+            unsigned cnt = 0;
+            if (i < nh) {
+                const unsigned a_s = hits[i] * V;
+                const uint4* __restrict__ col = reinterpret_cast<const uint4*>(sc + a_s);
+                const size_t rowv = (size_t)A / V;
+                float best[V];
+                int bc[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bc[k] = 0; }
-            int cc = 0;
-            for (; cc + SCAN_UNROLL <= nc; cc += SCAN_UNROLL) {
-                ScoreVec<T> v[SCAN_UNROLL];
+                for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bc[k] = 0; }
+                int cc = 0;
+                for (; cc + SCAN_UNROLL <= nc; cc += SCAN_UNROLL) {
+                    ScoreVec<T> v[SCAN_UNROLL];
 #pragma unroll
-                for (int u = 0; u < SCAN_UNROLL; ++u) v[u].raw = __ldg(col + (size_t)(cc + u) * rowv);
+                    for (int u = 0; u < SCAN_UNROLL; ++u) v[u].raw = __ldg(col + (size_t)(cc + u) * rowv);
 #pragma unroll
-                for (int u = 0; u < SCAN_UNROLL; ++u)
+                    for (int u = 0; u < SCAN_UNROLL; ++u)
+#pragma unroll
+                        for (int k = 0; k < V; ++k) {
+                            const float sv = to_f32<T>(v[u].e[k]);
+                            if ((cc + u) == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc + u; }  // lowest index wins ties
+                        }
+                }
+                for (; cc < nc; ++cc) {
+                    ScoreVec<T> v1;
+                    v1.raw = __ldg(col + (size_t)cc * rowv);
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        const float sv = to_f32<T>(v[u].e[k]);
-                        if ((cc + u) == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc + u; }  // lowest index wins ties
+                        const float sv = to_f32<T>(v1.e[k]);
+                        if (cc == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc; }
                     }
-            }
-            for (; cc < nc; ++cc) {
-                ScoreVec<T> v1;
-                v1.raw = __ldg(col + (size_t)cc * rowv);
+                }
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
-                    const float sv = to_f32<T>(v1.e[k]);
-                    if (cc == 0 || sv > best[k]) { best[k] = sv; bc[k] = cc; }
+                    mykeys[k] = 0ull;
+                    const unsigned sb = make_sbits(best[k]);
+                    if (sb - sb_lo <= sb_hi - sb_lo) {
+                        if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
+                        const u64 key = make_key(sb, (a_s + k) * (unsigned)nc + (unsigned)bc[k]);
+                        if (key >= lo && key < hi) { mykeys[k] = key; ++cnt; }
+                    }
                 }
-            }
+            } else {
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const unsigned sb = make_sbits(best[k]);
-                if (sb - sb_lo <= sb_hi - sb_lo) {
-                    if (filt && !((P.class_mask[bc[k] >> 5] >> (bc[k] & 31)) & 1u)) continue;
-                    f(sb, (int)(a_s + k), bc[k]);
-                }
+                for (int k = 0; k < V; ++k) mykeys[k] = 0ull;
             }
+            unsigned pos = warp_reserve(counter, cnt);
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                if (mykeys[k]) {
+                    if (pos < NMS_CAP) keys[pos] = mykeys[k];
+                    ++pos;
+                }
         }
     }
+    PROFX(14);  // collect: pass 2 (this thread)
     return true;
 }
 
@@ -812,6 +904,9 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
     auto collect = [&](u64 lo, u64 hi) -> unsigned {
         if (tid == 0) S.counter = 0;
         __syncthreads();
+#ifdef NMS_PROFILE
+        if (blockIdx.x == 0 && tid == 0) g_prof_t = clock64();
+#endif
         const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
         auto put = [&](unsigned sb, int a, int c) {
             const u64 key = make_key(sb, (unsigned)(a * nc + c));
@@ -822,7 +917,8 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
         };
         bool done = false;
         if (smax && !summary_dense)
-            done = for_each_candidate_summary<T, MULTI, true>(img, smax, nc, A, thr, P, put, sb_lo, sb_hi, S.g1, &S.nhits);
+            done = for_each_candidate_summary<T, MULTI, true>(img, smax, nc, A, thr, P, put, sb_lo, sb_hi, S.g1, &S.nhits,
+                                                              lo, hi, S.keys, &S.counter);
         if (!done) {
             summary_dense = true;  // candidates are dense in this segment: the plain scan is the better tool
             for_each_candidate<T, MULTI>(img, nc, A, thr, P, put, sb_lo, sb_hi);
