@@ -304,3 +304,51 @@ def test_full_size_properties_cfg3(ops):
     for (t, b) in [(0, 0), (1, 17), (2, 63)]:
         want = rp.nms_port(ys[t][b : b + 1].cpu(), greedy="c", **kw)[0]
         assert torch.equal(dets[t, b, : counts_h[t, b]].cpu(), want)
+
+
+# ------------------------------------------------------------------ shapes beyond the BASELINE configs
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("nc,imgsz,strides,bsz", [
+    (80, (256, 256), (8.0, 16.0, 32.0), 2),            # COCO-sized head: 3 class chunks in the decode grid
+    (365, (128, 192), (8.0, 16.0, 32.0), 1),           # Objects365-full head (reference data/voc_obj365_full.yaml)
+    (5, (512, 384), (8.0, 16.0, 32.0, 64.0), 2),       # four levels (P3-P6)
+    (1, (1280, 736), (8.0, 16.0, 32.0), 1),            # single class, non-square 1280 input
+])
+def test_decode_and_nms_other_head_shapes(ops, dtype, nc, imgsz, strides, bsz):
+    from cerberusdet_b200.nms import non_max_suppression
+    from oracle import ref_port as rp
+
+    heads = synth_heads(range(bsz), [nc], imgsz, dtype, "iid", cfg=31, strides=strides)
+    y = ops.decode_heads([[_dev(x) for x in heads[0]]], strides)[0]
+    ref = rp.decode_port(heads[0], nc, strides)
+    ok, msg = check_decode(y, ref, level_shapes(imgsz, strides), strides, nc)
+    assert ok, msg
+    for kw in (dict(conf_thres=0.01, iou_thres=0.6, multi_label=True, max_det=300),
+               dict(conf_thres=0.1, iou_thres=0.45, max_det=100),
+               dict(conf_thres=0.01, iou_thres=0.5, multi_label=True, classes=[0, nc - 1, nc // 2], max_det=50)):
+        want = rp.nms_port(y.cpu(), greedy="c", **kw)   # selection is bit exact on the SAME decoded tensor
+        got = non_max_suppression(y, **kw)
+        _assert_rows_equal(got, want, f"nc={nc} {kw}")
+
+
+def test_full_size_cfg2_and_cfg4(ops):
+    """BASELINE configs 2 (B=32, 2 tasks, best class, conf 0.3) and 4 (B=16, 1280^2, 33600 anchors, multi-label) at
+    full size: properties on every segment + bit-exact spot checks against the oracle."""
+    from oracle import ref_port as rp
+
+    for ncs, bsz, imgsz, kw in (([20, 19], 32, 640, dict(conf_thres=0.3, iou_thres=0.45, max_det=300)),
+                                ([20, 19, 12], 16, 1280, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300))):
+        heads = synth_heads(range(bsz), ncs, imgsz, torch.float16, "iid", cfg=3)
+        ys = ops.decode_heads([[_dev(x) for x in lv] for lv in heads], STRIDES)
+        dets, counts = ops.nms_batched(ys, **kw)
+        ch = counts.cpu()
+        assert (ch <= 300).all() and (ch > 0).all()
+        s = dets[..., 4]
+        for t in range(len(ncs)):
+            for b in range(bsz):
+                n = int(ch[t, b])
+                assert (s[t, b, : n - 1] >= s[t, b, 1:n]).all()
+                assert (dets[t, b, n:] == 0).all()          # padding rows are zeroed by the kernel
+        for (t, b) in [(0, 0), (len(ncs) - 1, bsz - 1)]:
+            want = rp.nms_port(ys[t][b : b + 1].cpu(), greedy="c", **kw)[0]
+            assert torch.equal(dets[t, b, : int(ch[t, b])].cpu(), want)
