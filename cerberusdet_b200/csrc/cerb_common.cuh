@@ -15,7 +15,18 @@
 // marks those rounding points (identity for float).
 template <typename T> __device__ __forceinline__ float rnd(float v);
 template <> __device__ __forceinline__ float rnd<float>(float v) { return v; }
-template <> __device__ __forceinline__ float rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
+// (packed convert: F2FP runs on the ALU pipes, the scalar F2F.F16.F32 on the SFU pipe the exps already load)
+template <> __device__ __forceinline__ float rnd<__half>(float v) { return __low2float(__floats2half2_rn(v, 0.f)); }
+
+// two roundings at once: for half one F2FP.PACK_AB packs both values (the compiler does not pair scalar
+// conversions by itself), for float nothing happens
+template <typename T> __device__ __forceinline__ void rnd2(float a, float b, float& ra, float& rb);
+template <> __device__ __forceinline__ void rnd2<float>(float a, float b, float& ra, float& rb) { ra = a; rb = b; }
+template <> __device__ __forceinline__ void rnd2<__half>(float a, float b, float& ra, float& rb) {
+    const float2 f = __half22float2(__floats2half2_rn(a, b));
+    ra = f.x;
+    rb = f.y;
+}
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
@@ -23,7 +34,7 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __low2half(__floats2half2_rn(v, 0.f)); }
 
 __device__ __forceinline__ float fast_ex2(float x) {
 #ifdef CERB_EXPERIMENT_NO_MUFU  // tools/ only: where does the time go without the SFU?
@@ -72,10 +83,13 @@ template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int k = 0; k < CERB_REG_MAX; k += 4) {
-        a0 = fmaf((float)k, rnd<T>(x[k] * inv), a0);
-        a1 = fmaf((float)(k + 1), rnd<T>(x[k + 1] * inv), a1);
-        a2 = fmaf((float)(k + 2), rnd<T>(x[k + 2] * inv), a2);
-        a3 = fmaf((float)(k + 3), rnd<T>(x[k + 3] * inv), a3);
+        float p0, p1, p2, p3;
+        rnd2<T>(x[k] * inv, x[k + 1] * inv, p0, p1);
+        rnd2<T>(x[k + 2] * inv, x[k + 3] * inv, p2, p3);
+        a0 = fmaf((float)k, p0, a0);
+        a1 = fmaf((float)(k + 1), p1, a1);
+        a2 = fmaf((float)(k + 2), p2, a2);
+        a3 = fmaf((float)(k + 3), p3, a3);
     }
     return rnd<T>((a0 + a1) + (a2 + a3));
 }
