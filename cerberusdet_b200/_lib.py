@@ -21,6 +21,7 @@ EXPORTS = (
     "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
+    "cerb_decode_nms",
     "cerb_cross_task",
     "cerb_debug_set_chunking",
     "cerb_debug_set_hist_sample",
@@ -58,6 +59,8 @@ def load() -> ctypes.CDLL:
     lib.cerb_nms_workspace_bytes.argtypes = [i, i, i]
     lib.cerb_nms.restype = i
     lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp]
+    lib.cerb_decode_nms.restype = i
+    lib.cerb_decode_nms.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_cross_task.restype = i
     lib.cerb_cross_task.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp]
     lib.cerb_debug_set_chunking.restype = i

@@ -249,3 +249,18 @@ extern "C" int cerb_cross_task(const float* dets, const int* counts, int T, int 
     }
     return 0;
 }
+
+extern "C" int cerb_decode_nms(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
+                               const float* strides, int dtype, void* const* y, void* const* smax, double conf_thres,
+                               double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
+                               int max_det, int max_nms, double max_wh, float* dets, int* counts, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    int written = 0;
+    int rc = cerb_decode(lvl, nc, T, L, B, H, W, strides, dtype, y, smax, &written, stream);
+    if (rc) return rc;
+    long A = 0;
+    for (int l = 0; l < L; ++l) A += (long)H[l] * W[l];
+    return cerb_nms((const void* const*)y, nc, T, B, (int)A, dtype, conf_thres, iou_thres, classes, n_classes, agnostic,
+                    multi_label, max_det, max_nms, max_wh, written ? (const void* const*)smax : nullptr, dets, counts,
+                    workspace, workspace_bytes, stream);
+}

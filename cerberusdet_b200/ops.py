@@ -282,3 +282,41 @@ def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Se
                                  out_counts.data_ptr(), _stream_ptr(dets.device))
     _lib.check(rc)
     return out, out_counts
+
+
+def decode_nms(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float], conf_thres: float = 0.25,
+               iou_thres: float = 0.45, classes: Optional[Sequence[int]] = None, agnostic: bool = False,
+               multi_label: bool = False, max_det: int = 300, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
+    """Raw head tensors -> padded detections in ONE library call (``cerb_decode_nms``: both kernels back to back on
+    the current stream).  Returns ``(dets[T,B,max_det,6], counts[T,B], ys)``."""
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    lib = _lib.load()
+    T, L = len(task_levels), len(strides)
+    first = task_levels[0][0]
+    _require_cuda(first, "head tensors")
+    code = _dtype_code(first)
+    B = int(first.shape[0])
+    H = [int(x.shape[2]) for x in task_levels[0]]
+    W = [int(x.shape[3]) for x in task_levels[0]]
+    A = sum(h * w for h, w in zip(H, W))
+    nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
+    lv = [x.contiguous() for row in task_levels for x in row]
+    dev = first.device
+    ys = [torch.empty((B, 4 + n, A), dtype=first.dtype, device=dev) for n in nc]
+    R = int(lib.cerb_summary_row_len(A, code))
+    sm = [torch.empty((B, n, max(R, 1)), dtype=first.dtype, device=dev) for n in nc]
+    dets = torch.empty((T, B, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((T, B), dtype=torch.int32, device=dev)
+    ws_bytes = lib.cerb_nms_workspace_bytes(T, B, max_det)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        rc = lib.cerb_decode_nms(
+            _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(nc), T, L, B, _lib.int_array(H), _lib.int_array(W),
+            _lib.float_array([float(s) for s in strides]), code, _lib.ptr_array([y.data_ptr() for y in ys]),
+            _lib.ptr_array([x.data_ptr() for x in sm]) if R else None, float(conf_thres), float(iou_thres),
+            _lib.int_array(list(classes)) if classes is not None else None, len(classes) if classes is not None else 0,
+            int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh), dets.data_ptr(),
+            counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(dev))
+    _lib.check(rc)
+    return dets, counts, ys

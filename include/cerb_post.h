@@ -101,6 +101,19 @@ int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dt
              size_t workspace_bytes, void* stream);
 
 /*
+ * Decode + NMS for T task heads in one call (two launches on `stream`, no host work in between): the raw head
+ * tensors go in, the padded detections come out; `y` (and `smax`, may be NULL) are caller-provided buffers that
+ * receive the decoded predictions / score summary on the way (they are what Detect.forward would have returned).
+ * Replaces the pair Detect.forward -> non_max_suppression as driven by
+ * cerberusdet/cerberusdet_inference.py:117-135.  Arguments as in cerb_decode and cerb_nms.
+ */
+int cerb_decode_nms(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
+                    const float* strides, int dtype, void* const* y, void* const* smax, double conf_thres,
+                    double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
+                    int max_nms, double max_wh, float* dets, int* counts, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
  * Cross-task merge of the per-task NMS results for a whole batch in one launch (one CTA per image).
  * Replaces the per-image host loop of CerberusDetInference.predict
  * (cerberusdet/cerberusdet_inference.py:140-155): _combine_output (:72-83, local -> global class ids),

@@ -352,3 +352,15 @@ def test_full_size_cfg2_and_cfg4(ops):
         for (t, b) in [(0, 0), (len(ncs) - 1, bsz - 1)]:
             want = rp.nms_port(ys[t][b : b + 1].cpu(), greedy="c", **kw)[0]
             assert torch.equal(dets[t, b, : int(ch[t, b])].cpu(), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_decode_nms_single_call_equals_two_calls(ops, dtype):
+    heads = synth_heads(range(4), [20, 19, 12], (320, 320), dtype, "iid", cfg=41)
+    dev = [[_dev(x) for x in lv] for lv in heads]
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
+    d1, c1, ys1 = ops.decode_nms(dev, STRIDES, **kw)
+    ys2 = ops.decode_heads(dev, STRIDES)
+    d2, c2 = ops.nms_batched(ys2, **kw)
+    assert all(torch.equal(a, b) for a, b in zip(ys1, ys2))
+    assert torch.equal(c1, c2) and torch.equal(d1, d2)

@@ -36,6 +36,8 @@ def test_argument_validation_without_gpu():
     rc = lib.cerb_nms(_lib.ptr_array([0]), _lib.int_array([5]), 1, 1, 10, 7, 0.25, 0.45, None, 0, 0, 0, 300, 30000,
                       7680.0, None, None, None, None, 0, None)
     assert rc == _lib.CERB_EINVAL and b"dtype" in lib.cerb_last_error()
+    rc = lib.cerb_cross_task(None, None, 3, 2, 400, _lib.int_array([0, 20, 39]), 0.8, None, None, None, None)
+    assert rc == _lib.CERB_EINVAL and b"1024" in lib.cerb_last_error()
     rc = lib.cerb_nms(_lib.ptr_array([0]), _lib.int_array([5]), 1, 1, 10, 0, 1.5, 0.45, None, 0, 0, 0, 300, 30000,
                       7680.0, None, None, None, None, 0, None)
     assert rc == _lib.CERB_EINVAL and lib.cerb_last_error().startswith(b"Invalid Confidence threshold")
