@@ -187,6 +187,36 @@ def main():
                             counts=counts.tolist(), dtype="float32")
         print(nm, counts.tolist(), rows[:, :4].tolist())
 
+    # BASELINE config 1: the REAL 2-task CerberusDet (yolov8x_voc_obj365.yaml, random init, 105.4 M parameters) built
+    # and split exactly as the reference does (utils/models_manager.py:199-213), one image, fp32, on the CPU.  Its
+    # Detect heads give both the raw per-level tensors and y, i.e. a decode vector produced by the unmodified model
+    # graph, and its scores (~6e-4, bias init models/yolo.py:110) give an NMS vector with > 30000 near-tied candidates.
+    # 320x320 instead of 640x640 keeps the fixture small (2100 anchors).
+    import copy
+
+    import cerberusdet.models.cerberus as cerb_mod
+
+    torch.manual_seed(0)
+    model = cerb_mod.CerberusDet(task_ids=["voc", "objects365_animals"], nc=[20, 19],
+                                 cfg=os.path.join(os.environ.get("CERB_REFERENCE_ROOT", "/root/reference"),
+                                                  "cerberusdet/models/yolov8x_voc_obj365.yaml"), ch=3, verbose=False)
+    model.sequential_split(copy.deepcopy(model.yaml["cerber"]), "cpu")
+    model.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = model(torch.rand(1, 3, 320, 320))
+    kw = dict(conf_thres=0.0003, iou_thres=0.6, multi_label=True)
+    for task, (y, xs) in out.items():
+        nm = f"model_cfg1_320_{task}"
+        stable = reference_nms(ref, y, True, **kw)
+        plain = reference_nms(ref, y, False, **kw)
+        rows, counts = _pack(stable)
+        np.savez_compressed(os.path.join(OUT, nm + ".npz"), **{f"level{i}": _np(t) for i, t in enumerate(xs)},
+                            y=_np(y), pred=_np(y), rows=rows, counts=counts)
+        manifest[nm] = dict(kind="model", nc=int(y.shape[1] - 4), imgsz=[320, 320], bsz=1, dtype="float32", kwargs=kw,
+                            plain_equal=bool(torch.equal(stable[0], plain[0])), counts=counts.tolist())
+        print(nm, tuple(y.shape), counts.tolist(), "plain_equal", manifest[nm]["plain_equal"])
+
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -364,3 +364,20 @@ def test_decode_nms_single_call_equals_two_calls(ops, dtype):
     d2, c2 = ops.nms_batched(ys2, **kw)
     assert all(torch.equal(a, b) for a, b in zip(ys1, ys2))
     assert torch.equal(c1, c2) and torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_real_model_config1_vectors_gpu(ops, name):
+    """BASELINE config 1 on the GPU path: raw head tensors of the real 2-task CerberusDet model -> decode within
+    tolerance of the model's own y; NMS of the model's y bit-exact (> 30000 near-tied fp32 candidates)."""
+    from cerberusdet_b200.nms import non_max_suppression
+
+    g = load_golden(name)
+    meta = golden_manifest()[name]
+    levels = [torch.from_numpy(g[f"level{i}"]) for i in range(3)]
+    ref_y = torch.from_numpy(g["y"])
+    y = ops.decode_heads([[_dev(x) for x in levels]], STRIDES)[0]
+    ok, msg = check_decode(y, ref_y, [x.shape[2:] for x in levels], STRIDES, meta["nc"])
+    assert ok, msg
+    got = non_max_suppression(_dev(ref_y), **meta["kwargs"])
+    _assert_rows_equal(got, split_rows(g["rows"], g["counts"]), name)

@@ -69,3 +69,17 @@ def test_asserts_like_reference():
         rp.nms_port(pred, conf_thres=1.5)
     with pytest.raises(AssertionError):
         rp.nms_port(pred, iou_thres=-0.1)
+
+
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_real_model_config1_vectors(name):
+    """BASELINE config 1: vectors produced by the real 2-task CerberusDet model graph (random init) on the CPU."""
+    g = load_golden(name)
+    meta = golden_manifest()[name]
+    levels = [torch.from_numpy(g[f"level{i}"]) for i in range(3)]
+    y = rp.decode_port(levels, meta["nc"], STRIDES)
+    assert torch.equal(y, torch.from_numpy(g["y"]))
+    for greedy in ("torchvision", "c"):
+        got = rp.nms_port(y, greedy=greedy, **meta["kwargs"])
+        want = split_rows(g["rows"], g["counts"])
+        assert len(got) == 1 and torch.equal(got[0], want[0])
