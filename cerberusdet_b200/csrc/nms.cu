@@ -862,6 +862,9 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
                     int changed = 0;
                     if (lane == 0) { S.keep32[cur ^ 1][wid] = mine; changed = (mine != K[wid]); }
                     cur ^= 1;
+#ifdef NMS_PROFILE
+                    if (blockIdx.x == 0 && tid == 0) g_nms_prof[15] += 1;  // fixpoint block rounds
+#endif
                     if (!__syncthreads_or(changed)) break;
                 }
             }
@@ -985,7 +988,10 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
         const unsigned base = S.g0[hi0];
         const unsigned rem_s = S.g0[0] - base;  // candidates left below hi0, in histogram units
         if (exact && rem_s == 0) break;
-        const unsigned need = min(target, max_nms - consumed);
+        unsigned need = min(target, max_nms - consumed);
+        // an estimating histogram (summary: a lower bound; sample: noisy) must leave head-room below the capacity,
+        // or the gather overflows and the segment pays for an exact histogram
+        if (!exact) need = min(need, cap - cap / 4 - cap / 8);
         const unsigned need_s = hstride == 1 ? need : (need + need / 4 + hstride - 1) / hstride;  // sample: +25% margin
         int lo0 = 0;
         bool single_heavy = false;

@@ -26,6 +26,10 @@ def timeit(fn, n=30, warm=5, flush=None):
 
 def main():
     names = sys.argv[1:] or ["cfg2", "cfg3", "cfg4"]
+    if os.environ.get("CERB_CHUNKING"):  # "cap,first" -> test hook, e.g. CERB_CHUNKING=2048,369
+        from cerberusdet_b200 import _lib
+        cap, first = (int(v) for v in os.environ["CERB_CHUNKING"].split(","))
+        assert _lib.load().cerb_debug_set_chunking(cap, first) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name in names:
         c = CFG[name]

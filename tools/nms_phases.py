@@ -21,4 +21,4 @@ for name in sys.argv[1:] or ["cfg2", "cfg3"]:
     print(f"{name}: block0 cycles/run {tot/runs:.0f} (~{tot/runs/1.9e3:.1f} us @1.9GHz), consumed/run {buf[11]/runs:.0f}")
     for i, n in enumerate(names):
         print(f"   {n:14s} {buf[i]/runs:9.0f} cyc  {100*buf[i]/tot:5.1f}%")
-    print("   collect sub-steps (pass1, wait, pass2):", [round(buf[i] / runs) for i in range(12, 15)])
+    print("   collect sub-steps (pass1, wait, pass2):", [round(buf[i] / runs) for i in range(12, 15)], " fixpoint rounds/run:", buf[15] / runs)
