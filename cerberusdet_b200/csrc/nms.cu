@@ -1022,7 +1022,14 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
         consume_chunk(n, take);
         consumed += take;
         hi0 = lo0;
-        target = min(target * 4u, cap);
+        // next chunk: as many candidates as the keep rate seen so far says are needed to fill max_det (+25 %),
+        // at least double, at most the capacity
+        {
+            const unsigned missing = (unsigned)max(max_det - kept, 0);
+            const unsigned long long want = (unsigned long long)missing * consumed / (unsigned)max(kept, 1);
+            const unsigned adaptive = (unsigned)min(want + want / 4ull + 64ull, (unsigned long long)cap);
+            target = min(max(adaptive, min(target * 2u, cap)), cap);
+        }
     }
 
     if (tid == 0) P.counts[seg] = kept;
