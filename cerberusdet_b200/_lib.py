@@ -23,6 +23,7 @@ EXPORTS = (
     "cerb_nms",
     "cerb_decode_nms",
     "cerb_cross_task",
+    "cerb_val_match",
     "cerb_debug_set_chunking",
     "cerb_debug_set_hist_sample",
 )
@@ -63,6 +64,8 @@ def load() -> ctypes.CDLL:
     lib.cerb_decode_nms.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_cross_task.restype = i
     lib.cerb_cross_task.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp]
+    lib.cerb_val_match.restype = i
+    lib.cerb_val_match.argtypes = [vp, vp, i, i, vp, vp, i, fp, i, vp, vp]
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
     lib.cerb_debug_set_hist_sample.restype = i

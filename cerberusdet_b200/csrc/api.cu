@@ -264,3 +264,25 @@ extern "C" int cerb_decode_nms(const void* const* lvl, const int* nc, int T, int
                     multi_label, max_det, max_nms, max_wh, written ? (const void* const*)smax : nullptr, dets, counts,
                     workspace, workspace_bytes, stream);
 }
+
+extern "C" int cerb_val_match(const float* dets, const int* counts, int B, int max_det, const float* labels,
+                              const int* label_offsets, int max_labels_per_image, const float* iouv, int K,
+                              unsigned char* correct, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(B >= 0 && max_det >= 0, "cerb_val_match: negative size");
+    REQUIRE(K >= 1 && K <= 16, "cerb_val_match: K=%d thresholds outside [1, 16]", K);
+    REQUIRE(max_labels_per_image >= 0 && max_labels_per_image <= 1024, "cerb_val_match: more than 1024 labels per image (%d)", max_labels_per_image);
+    if (B == 0 || max_det == 0) return 0;
+    REQUIRE(dets && counts && label_offsets && iouv && correct, "cerb_val_match: null argument");
+    ValMatchParams P;
+    memset(&P, 0, sizeof(P));
+    P.dets = dets; P.counts = counts; P.labels = labels; P.label_offsets = label_offsets;
+    P.B = B; P.max_det = max_det; P.K = K; P.correct = correct;
+    for (int i = 0; i < K; ++i) P.iouv[i] = iouv[i];
+    cudaError_t e = cerb_launch_val_match(P, max_labels_per_image, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_val_match: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}

@@ -62,3 +62,15 @@ struct CrossTaskParams {
     int* out_counts;         // [B]
 };
 cudaError_t cerb_launch_cross_task(const CrossTaskParams& P, cudaStream_t stream);
+
+// ------------------------------------------------------------------ validation matching
+struct ValMatchParams {
+    const float* dets;          // [B, max_det, 6] native-space detections of ONE task (x1, y1, x2, y2, conf, cls)
+    const int* counts;          // [B]
+    const float* labels;        // [sum M_b, 5] (cls, x1, y1, x2, y2), images concatenated
+    const int* label_offsets;   // device [B + 1]
+    int B, max_det, K;
+    float iouv[16];             // IoU thresholds (val.py: linspace(0.5, 0.95, 10))
+    unsigned char* correct;     // [B, max_det, K]
+};
+cudaError_t cerb_launch_val_match(const ValMatchParams& P, int max_labels_per_image, cudaStream_t stream);

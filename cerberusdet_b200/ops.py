@@ -320,3 +320,31 @@ def decode_nms(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[
             counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(dev))
     _lib.check(rc)
     return dets, counts, ys
+
+
+def match_batch(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, label_offsets: Sequence[int],
+                iouv: torch.Tensor) -> torch.Tensor:
+    """Batched GPU form of the reference's ``process_batch`` (val.py:32-54): ``dets [B, max_det, 6]`` /
+    ``counts [B]`` of one task in native image space, ``labels [sum M_b, 5]`` (cls, x1, y1, x2, y2) with
+    ``label_offsets`` (``B+1`` python ints) -> ``correct [B, max_det, K]`` bool (device)."""
+    lib = _lib.load()
+    _require_cuda(dets, "dets")
+    B, max_det, _ = dets.shape
+    offs = [int(o) for o in label_offsets]
+    if len(offs) != B + 1:
+        raise ValueError("label_offsets must have B+1 entries")
+    mmax = max((offs[i + 1] - offs[i] for i in range(B)), default=0)
+    if mmax > 1024:
+        raise ValueError("match_batch supports at most 1024 labels per image")
+    dev = dets.device
+    dets, counts = dets.contiguous().float(), counts.contiguous().to(torch.int32)
+    labels = labels.to(device=dev, dtype=torch.float32).contiguous()
+    offs_d = torch.tensor(offs, dtype=torch.int32, device=dev)
+    iou_host = [float(v) for v in iouv.detach().cpu().float().tolist()]
+    K = len(iou_host)
+    correct = torch.empty((B, max_det, K), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cerb_val_match(dets.data_ptr(), counts.data_ptr(), B, max_det, labels.data_ptr() if labels.numel() else None,
+                                offs_d.data_ptr(), mmax, _lib.float_array(iou_host), K, correct.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc)
+    return correct.bool()

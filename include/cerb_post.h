@@ -131,6 +131,22 @@ int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_
                     double iou_thres, const float* scale, float* out, int* out_counts, void* stream);
 
 /*
+ * Which detections are correct at each IoU threshold, for a whole batch of ONE task in one launch (one CTA per image).
+ * Replaces process_batch (cerberusdet/val.py:32-54) as called per image by the validation loop (val.py:321-357).
+ *
+ *   dets, counts     [B, max_det, 6] / [B]: detections already in native image space (scale_boxes applied)
+ *   labels           device [sum_b M_b, 5] rows (cls, x1, y1, x2, y2), native space, images concatenated
+ *   label_offsets    device [B + 1] row offsets into labels; max_labels_per_image = max_b M_b (<= 1024)
+ *   iouv             host [K] thresholds (K <= 16; the reference uses linspace(0.5, 0.95, 10))
+ *   correct          out [B, max_det, K] bytes (0/1); rows past counts[b] are 0
+ * Equal IoUs of one detection with two labels resolve to the lower label index (the reference's numpy sort is
+ * unstable there).
+ */
+int cerb_val_match(const float* dets, const int* counts, int B, int max_det, const float* labels,
+                   const int* label_offsets, int max_labels_per_image, const float* iouv, int K,
+                   unsigned char* correct, void* stream);
+
+/*
  * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy
  * top-k so small inputs exercise the multi-chunk and radix-refinement paths.
  * (0, 0) restores the defaults.  Results never depend on these values.

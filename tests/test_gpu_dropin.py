@@ -210,3 +210,33 @@ def test_cross_task_merge_everything_deleted_keeps_everything():
     merged, mc = cross_task_merge(dets.cuda(), counts.cuda(), [0, 3], 0.5)
     want = ct.suppress_between_tasks(ct.combine_tasks({"a": dets[0, 0, :1], "b": dets[1, 0, :1]}, maps), maps, 0.5)
     assert int(mc[0]) == want.shape[0] and torch.equal(merged[0, : int(mc[0])].cpu(), want)
+
+
+def test_val_match_batch_matches_host_restatement():
+    """GPU process_batch for a whole batch == val_stats.match_predictions per image (itself pinned to the reference's
+    process_batch by tests/test_host_logic.py)."""
+    from test_host_logic import _val_case
+
+    from cerberusdet_b200.ops import match_batch
+    from cerberusdet_b200.val_stats import match_predictions
+
+    g = torch.Generator().manual_seed(3)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    B, md = 9, 300
+    dets = torch.zeros(B, md, 6)
+    counts = torch.zeros(B, dtype=torch.int32)
+    labs, offs, per = [], [0], []
+    for b in range(B):
+        M = 0 if b == 2 else int(torch.randint(1, 40, (1,), generator=g))
+        N = 0 if b == 5 else (300 if b == 7 else int(torch.randint(1, 120, (1,), generator=g)))
+        det, lab = _val_case(g, M, N, ncls=3)
+        dets[b, :N] = det
+        counts[b] = N
+        labs.append(lab)
+        offs.append(offs[-1] + M)
+        per.append((det, lab))
+    got = match_batch(dets.cuda(), counts.cuda(), torch.cat(labs, 0), offs, iouv).cpu()
+    for b, (det, lab) in enumerate(per):
+        want = match_predictions(det, lab, iouv)
+        assert torch.equal(got[b, : det.shape[0]], want), b
+        assert not got[b, det.shape[0]:].any()

@@ -208,3 +208,40 @@ def test_detection_gatherer_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHERER_OK" in outs[0]
+
+
+def _val_case(g, M, N, ncls=4):
+    c = torch.rand(M, 2, generator=g) * 300 + 50
+    wh = 40 + torch.rand(M, 2, generator=g) * 80
+    lab = torch.cat((torch.randint(0, ncls, (M, 1), generator=g).float(), c - wh / 2, c + wh / 2), 1)
+    if M and N:
+        pick = torch.randint(0, M, (N,), generator=g)
+        dc = c[pick] + torch.randn(N, 2, generator=g) * 8
+        dwh = wh[pick] * (1 + 0.15 * torch.randn(N, 2, generator=g)).clamp_min(0.2)
+        dcls = torch.where(torch.rand(N, generator=g) < 0.8, lab[pick, 0], torch.randint(0, ncls, (N,), generator=g).float())
+    else:
+        dc = torch.rand(N, 2, generator=g) * 300
+        dwh = torch.rand(N, 2, generator=g) * 50 + 10
+        dcls = torch.randint(0, ncls, (N,), generator=g).float()
+    conf = torch.rand(N, 1, generator=g).sort(0, descending=True).values
+    det = torch.cat((dc - dwh / 2, dc + dwh / 2, conf, dcls[:, None]), 1)
+    return det, lab
+
+
+@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+def test_val_matching_matches_reference_process_batch():
+    """val_stats.match_predictions == the reference's process_batch (cerberusdet/val.py:32-54)."""
+    from oracle.ref_import import load_reference
+
+    load_reference()
+    import cerberusdet.val as ref_val
+
+    from cerberusdet_b200.val_stats import match_predictions
+
+    g = torch.Generator().manual_seed(0)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    for trial in range(120):
+        M = int(torch.randint(1, 25, (1,), generator=g))
+        N = int(torch.randint(1, 60, (1,), generator=g))
+        det, lab = _val_case(g, M, N)
+        assert torch.equal(ref_val.process_batch(det, lab, iouv), match_predictions(det, lab, iouv)), trial
