@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
         const int W = P.w[level];
         const float st = P.stride[level];
         Pack<T, VEC> oc, os;
+        int gx = a0 % W, gy = a0 / W;  // one division per thread; the VEC anchors then walk the grid row by row
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const int a = a0 + i;
-            const int g = (part == 0) ? (a % W) : (a / W);
+            const int g = (part == 0) ? gx : gy;
+            if (++gx >= W) { gx = 0; ++gy; }
             const float ac = rnd<T>(rnd<T>((float)g) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
             const float p1 = rnd<T>(ac - dlo[i]);
             const float p2 = rnd<T>(ac + dhi[i]);
