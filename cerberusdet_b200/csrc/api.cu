@@ -64,7 +64,8 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
     DecodeParams P;
     memset(&P, 0, sizeof(P));
     P.T = T; P.L = L; P.B = B; P.nrows = T * L;
-    P.interleave_parts = dtype == CERB_F32 ? 1 : 0;
+    P.interleave_parts = dtype == CERB_F32 ? 1 : 2;  // measured best per dtype (profiles/r01_decode.md)
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_ORDER")) P.interleave_parts = atoi(ev);  // tools/ only
     const size_t elt = dtype == CERB_F16 ? 2 : 4;
     int vec = (int)(16 / elt);
     long A = 0;

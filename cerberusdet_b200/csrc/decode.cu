@@ -101,20 +101,24 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
         }
         row = lo;
     }
-    const int task = row / P.L, level = row - task * P.L;
+    const int TL = P.T * P.L;
+    const bool cls_row = row >= TL;  // box-first order only: rows TL.. are the class rows
+    const int trow = cls_row ? row - TL : row;
+    const int task = trow / P.L, level = trow - task * P.L;
     const int in_row = blockIdx.x - P.row_start[row];
-    const int bpp = P.row_blocks_per_part[row];
-    // Block order of the parts.  Contiguous ([all DFL l,r blocks][all t,b][classes]) is faster for fp16
-    // (81.5 vs 87.7 us); interleaved (DFL and class blocks share every SM at all times) is faster for fp32,
-    // which is HBM-bound (113.7 vs 118.8 us) -- profiles/r01_decode.md.
+    const int bpp = P.row_blocks_per_part[trow];
+    // Block order of the parts (profiles/r01_decode.md): 0 = contiguous per (task, level): [l,r blocks][t,b][classes];
+    // 1 = interleaved (DFL and class blocks share every SM at all times; best for fp32, which is HBM-bound);
+    // 2 = every DFL block of the launch first, then every class block (the short streaming blocks fill the tail).
     int part, vblk;
-    if (P.interleave_parts) {
+    if (P.interleave_parts == 1) {
         const int nparts = 2 + (P.nc[task] + CLS_CHUNK - 1) / CLS_CHUNK;
         vblk = in_row / nparts;
         part = in_row - vblk * nparts;
     } else {
         part = in_row / bpp;
         vblk = in_row - part * bpp;
+        if (cls_row) part += 2;
     }
 
     const int hw = P.hw[level];
@@ -216,16 +220,21 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
 
 template <typename T, int VEC> static cudaError_t launch_decode_t(DecodeParams& P, cudaStream_t stream) {
     int blocks = 0;
-    for (int t = 0; t < P.T; ++t)
-        for (int l = 0; l < P.L; ++l) {
-            const int row = t * P.L + l;
-            const long items = (long)P.B * (P.hw[l] / VEC);
-            const int bpp = (int)((items + DEC_THREADS - 1) / DEC_THREADS);
-            const int parts = 2 + (P.nc[t] + CLS_CHUNK - 1) / CLS_CHUNK;
-            P.row_start[row] = blocks;
-            P.row_blocks_per_part[row] = bpp > 0 ? bpp : 1;
-            blocks += bpp * parts;
-        }
+    const int TL = P.T * P.L;
+    const int passes = P.interleave_parts == 2 ? 2 : 1;  // box-first: DFL rows, then class rows
+    for (int pass = 0; pass < passes; ++pass)
+        for (int t = 0; t < P.T; ++t)
+            for (int l = 0; l < P.L; ++l) {
+                const int trow = t * P.L + l;
+                const long items = (long)P.B * (P.hw[l] / VEC);
+                const int bpp = (int)((items + DEC_THREADS - 1) / DEC_THREADS);
+                const int cls_parts = (P.nc[t] + CLS_CHUNK - 1) / CLS_CHUNK;
+                const int parts = passes == 1 ? 2 + cls_parts : (pass == 0 ? 2 : cls_parts);
+                P.row_start[pass * TL + trow] = blocks;
+                P.row_blocks_per_part[trow] = bpp > 0 ? bpp : 1;
+                blocks += bpp * parts;
+            }
+    P.nrows = passes * TL;
     P.row_start[P.nrows] = blocks;
     if (blocks == 0) return cudaSuccess;
     decode_kernel<T, VEC><<<blocks, DEC_THREADS, 0, stream>>>(P);
