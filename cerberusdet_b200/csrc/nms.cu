@@ -12,18 +12,28 @@
 //    descending key order == "score descending, candidate index ascending", the
 //    canonical form of the reference's sort at :459 (ties there are unspecified).
 //  * Greedy NMS is order-causal and stops at max_det (:465), so only a prefix of the
-//    sorted order is ever needed.  A 4096-bin histogram of the top 12 key bits (one pass
-//    over the scores, in shared memory) locates successive chunks of <= CAP keys; each
-//    chunk is gathered, bitonic-sorted in shared memory and consumed; the kernel stops
-//    as soon as max_det boxes are kept or max_nms candidates (:459) were consumed.
-//    A bin that alone exceeds CAP (massive ties) is refined by deeper radix levels.
+//    sorted order is ever needed.  A 2048-bin histogram of the top 12 key bits locates
+//    successive chunks of <= CAP keys; each chunk is gathered, bitonic-sorted (registers +
+//    shuffles + shared memory) and consumed; the kernel stops as soon as max_det boxes are
+//    kept or max_nms candidates (:459) were consumed.  The histogram only steers chunk
+//    sizes, so it may be an estimate: from the score summary the decode kernel leaves (one
+//    maximum per 16-byte score vector), or from every 8th score vector; what a chunk
+//    contains, its order and every count that matters are exact.  An overflowing chunk
+//    switches the segment to an exact histogram; a single bin that exceeds CAP (massive
+//    ties) is refined by deeper 12-bit radix levels down to unique keys.
+//  * Scans.  With a summary, pass 1 reads it (1/8 of the scores) and lists the score
+//    vectors whose maximum reaches the chunk's lower bound, pass 2 reads only those; list
+//    and key slots are reserved per warp (count, prefix-sum, one atomic).  Without a
+//    summary, or when the candidates are dense, the class planes are scanned with 128-bit
+//    loads and a packed-half2 range prefilter.
 //  * Suppression (:462-465): candidates are taken in tiles of 512, one per thread; a
 //    candidate is first tested against the kept list (shared memory), then the tile is
 //    resolved internally with a per-thread suppressor bitmask and a ballot fixpoint
 //    iteration (equal to the sequential sweep).  Per-class chains skip the pairs that the
-//    class offset makes disjoint.  IoU arithmetic reproduces
-//    torchvision's CPU kernel: separately rounded fp32 ops on class-offset boxes, strict
-//    '>' against the threshold (the double-precision compare is folded into iou_thr).
+//    class offset makes disjoint.  IoU arithmetic reproduces torchvision's CPU kernel:
+//    separately rounded fp32 ops on class-offset boxes, strict '>' against the threshold
+//    (the double-precision compare is folded into iou_thr).
+//  History, counters and the experiments that did not work: profiles/r01_nms.md.
 #include "cerb_kernels.h"
 
 #define NMS_THREADS 512
