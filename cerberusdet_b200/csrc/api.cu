@@ -26,6 +26,15 @@ void cerb_set_error(const char* fmt, ...) {
         }                             \
     } while (0)
 
+// default decode kernel per dtype (profiles/r02_decode.md): items per thread of the pipelined kernel, 0 = decode.cu's
+#ifndef CERB_DECODE_PIPE_F16
+#define CERB_DECODE_PIPE_F16 0
+#endif
+#ifndef CERB_DECODE_PIPE_F32
+#define CERB_DECODE_PIPE_F32 0
+#endif
+#define CERB_DECODE_PIPE_DEFAULT(dtype) ((dtype) == CERB_F16 ? CERB_DECODE_PIPE_F16 : CERB_DECODE_PIPE_F32)
+
 static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 extern "C" int cerb_version(void) { return 100; }
@@ -110,6 +119,10 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
     bool use_tma = false;
     if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = vec == (int)(16 / elt) && atoi(ev) != 0;  // tools/ only
     if (use_tma) e = cerb_launch_decode_tma(P, dtype, (cudaStream_t)stream);
+    // software-pipelined kernel (decode_pipe.cu): items per thread, 0 = the register-resident kernel
+    int pipe_ipt = CERB_DECODE_PIPE_DEFAULT(dtype);
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_PIPE")) pipe_ipt = atoi(ev);  // tools/ and tests only
+    if (!use_tma && pipe_ipt > 0 && vec == (int)(16 / elt)) e = cerb_launch_decode_pipe(P, dtype, pipe_ipt, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) {
         (void)cudaGetLastError();
         e = cerb_launch_decode(P, dtype, vec, (cudaStream_t)stream);

@@ -22,6 +22,9 @@ struct DecodeParams {
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
 // persistent TMA-pipelined variant; needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one
 cudaError_t cerb_launch_decode_tma(const DecodeParams& P, int dtype, cudaStream_t stream);
+// software-pipelined variant (cp.async prefetch into per-thread shared-memory slots, ipt items per thread);
+// needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one
+cudaError_t cerb_launch_decode_pipe(const DecodeParams& P, int dtype, int ipt, cudaStream_t stream);
 
 // ------------------------------------------------------------------ select + NMS
 #define CERB_MAX_CLASS_WORDS 32  // class filter bitmask: nc <= 1024

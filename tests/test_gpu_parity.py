@@ -55,6 +55,39 @@ def test_decode_vs_oracle_multitask(ops, dtype, imgsz, bsz):
         assert ok, f"task {t}: {msg}"
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("ipt", [1, 2, 4])
+def test_decode_pipelined_kernel_bit_identical_to_register_kernel(ops, dtype, ipt, monkeypatch):
+    """decode_pipe.cu (cp.async prefetch, ipt items per thread) and decode.cu do the same arithmetic: y and the score
+    summary must be bit-identical, on ragged item counts (B * hw / VEC not a multiple of 128 * ipt), several class
+    group remainders (nc % 4 = 0, 3, 1, 2) and more than one class group ring turn (nc = 80)."""
+    from cerberusdet_b200 import ops as o
+
+    for ncs, imgsz, bsz in [([20, 19, 12], (640, 640), 3), ([80, 5, 1, 2], (96, 72), 5), ([19], (1280, 736), 1)]:
+        heads = synth_heads(range(bsz), ncs, imgsz, dtype, "iid", cfg=77)
+        dev = [[_dev(x) for x in lv] for lv in heads]
+        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", "0")
+        y0 = ops.decode_heads(dev, STRIDES)
+        s0 = [o.find_summary(y) for y in y0]
+        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", str(ipt))
+        y1 = ops.decode_heads(dev, STRIDES)
+        s1 = [o.find_summary(y) for y in y1]
+        for t in range(len(ncs)):
+            assert torch.equal(y0[t], y1[t]), f"y differs: task {t} ncs={ncs} imgsz={imgsz}"
+            assert (s0[t] is None) == (s1[t] is None)
+            if s0[t] is not None:
+                n = y0[t].shape[2] // (8 if dtype == torch.float16 else 4)  # the padding past A / V is never written
+                assert torch.equal(s0[t][..., :n], s1[t][..., :n]), f"summary differs: task {t} ncs={ncs}"
+    # and against the oracle directly
+    from oracle import ref_port as rp
+
+    heads = synth_heads(range(2), [20, 19, 12], (640, 640), dtype, "iid", cfg=21)
+    ys = ops.decode_heads([[_dev(x) for x in lv] for lv in heads], STRIDES)
+    for t, nc in enumerate([20, 19, 12]):
+        ok, msg = check_decode(ys[t], rp.decode_port(heads[t], nc, STRIDES), level_shapes((640, 640), STRIDES), STRIDES, nc)
+        assert ok, f"task {t}: {msg}"
+
+
 def test_decode_rejects_cpu_and_bad_shapes(ops):
     heads = synth_heads(range(1), [20], 64, torch.float32)
     with pytest.raises(TypeError):
