@@ -26,12 +26,12 @@ void cerb_set_error(const char* fmt, ...) {
         }                             \
     } while (0)
 
-// default decode kernel per dtype (profiles/r02_decode.md): items per thread of the pipelined kernel, 0 = decode.cu's
+// default decode kernel per dtype (profiles/r01_decode.md, "software-pipelined variant"): items per thread of the pipelined kernel, 0 = decode.cu's
 #ifndef CERB_DECODE_PIPE_F16
-#define CERB_DECODE_PIPE_F16 0
+#define CERB_DECODE_PIPE_F16 2
 #endif
 #ifndef CERB_DECODE_PIPE_F32
-#define CERB_DECODE_PIPE_F32 0
+#define CERB_DECODE_PIPE_F32 1
 #endif
 #define CERB_DECODE_PIPE_DEFAULT(dtype) ((dtype) == CERB_F16 ? CERB_DECODE_PIPE_F16 : CERB_DECODE_PIPE_F32)
 

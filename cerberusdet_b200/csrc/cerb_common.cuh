@@ -55,6 +55,40 @@ __device__ __forceinline__ float fast_rcp(float x) {
 #endif
 }
 
+// ---- mixed-precision FMA (sm_100a, PTX fma.rn.f32.f16 -> SASS FHFMA): d = a.f16 * b.f16 + c.f32, a and b picked
+// from the low / high half of a packed register, one rounding in fp32
+__device__ __forceinline__ float fhfma_lo(uint32_t a2, uint32_t b2, float c) {
+    float d;
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+        "fma.rn.f32.f16 %0, al, bl, %3;\n\t}"
+        : "=f"(d) : "r"(a2), "r"(b2), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a2, uint32_t b2, float c) {
+    float d;
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+        "fma.rn.f32.f16 %0, ah, bh, %3;\n\t}"
+        : "=f"(d) : "r"(a2), "r"(b2), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_half2_rn(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// packed half2 bit pattern of two small non-negative integers (exact in half), a compile-time constant after unrolling
+__host__ __device__ constexpr uint32_t half_bits_of_int(int k) {
+    // k in [0, 2048): sign 0, exponent 15 + floor(log2 k), mantissa = the bits below the leading one
+    if (k == 0) return 0u;
+    int e = 0;
+    for (int t = k; t > 1; t >>= 1) ++e;
+    return (uint32_t)((15 + e) << 10) | (((uint32_t)k << (10 - e)) & 0x3FFu);
+}
+__host__ __device__ constexpr uint32_t half2_bits_of_ints(int lo, int hi) {
+    return half_bits_of_int(lo) | (half_bits_of_int(hi) << 16);
+}
+static_assert(half_bits_of_int(1) == 0x3C00 && half_bits_of_int(3) == 0x4200 && half_bits_of_int(9) == 0x4880 &&
+              half_bits_of_int(15) == 0x4B80, "half encoding of the DFL bin weights");
+
 // Expected DFL distance of one box side: sum_k k * softmax(x)_k over the 16 bins (reference DFL.forward,
 // models/yolo.py:57-59).  Rounding points follow the reference for half tensors: probabilities are rounded
 // to half (softmax output), the frozen 1x1 conv accumulates in fp32 and rounds once.  Max, sum and the
@@ -81,15 +115,32 @@ template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x
     const float s3 = (x[12] + x[13]) + (x[14] + x[15]);
     const float inv = fast_rcp((s0 + s1) + (s2 + s3));
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#ifndef CERB_NO_FHFMA
+    if constexpr (sizeof(T) == 2) {
+        // half: the rounded probabilities stay packed and feed the mixed-precision FMA (FHFMA: f16 x f16 + f32, one
+        // rounding) -- the same value as fmaf((float)k, (float)p, acc) without the two unpacking converts per pair
 #pragma unroll
-    for (int k = 0; k < CERB_REG_MAX; k += 4) {
-        float p0, p1, p2, p3;
-        rnd2<T>(x[k] * inv, x[k + 1] * inv, p0, p1);
-        rnd2<T>(x[k + 2] * inv, x[k + 3] * inv, p2, p3);
-        a0 = fmaf((float)k, p0, a0);
-        a1 = fmaf((float)(k + 1), p1, a1);
-        a2 = fmaf((float)(k + 2), p2, a2);
-        a3 = fmaf((float)(k + 3), p3, a3);
+        for (int k = 0; k < CERB_REG_MAX; k += 4) {
+            const uint32_t p01 = pack_half2_rn(x[k] * inv, x[k + 1] * inv);
+            const uint32_t p23 = pack_half2_rn(x[k + 2] * inv, x[k + 3] * inv);
+            if (k != 0) a0 = fhfma_lo(p01, half2_bits_of_ints(k, k + 1), a0);  // 0 * p0 + 0 == +0
+            a1 = fhfma_hi(p01, half2_bits_of_ints(k, k + 1), a1);
+            a2 = fhfma_lo(p23, half2_bits_of_ints(k + 2, k + 3), a2);
+            a3 = fhfma_hi(p23, half2_bits_of_ints(k + 2, k + 3), a3);
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < CERB_REG_MAX; k += 4) {
+            float p0, p1, p2, p3;
+            rnd2<T>(x[k] * inv, x[k + 1] * inv, p0, p1);
+            rnd2<T>(x[k + 2] * inv, x[k + 3] * inv, p2, p3);
+            a0 = fmaf((float)k, p0, a0);
+            a1 = fmaf((float)(k + 1), p1, a1);
+            a2 = fmaf((float)(k + 2), p2, a2);
+            a3 = fmaf((float)(k + 3), p3, a3);
+        }
     }
     return rnd<T>((a0 + a1) + (a2 + a3));
 }
