@@ -24,6 +24,8 @@ EXPORTS = (
     "cerb_decode_nms",
     "cerb_cross_task",
     "cerb_val_match",
+    "cerb_bbox_decode_fwd",
+    "cerb_bbox_decode_bwd",
     "cerb_debug_set_chunking",
     "cerb_debug_set_hist_sample",
 )
@@ -66,6 +68,11 @@ def load() -> ctypes.CDLL:
     lib.cerb_cross_task.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp]
     lib.cerb_val_match.restype = i
     lib.cerb_val_match.argtypes = [vp, vp, i, i, vp, vp, i, fp, i, vp, vp]
+    lg = ctypes.c_long
+    lib.cerb_bbox_decode_fwd.restype = i
+    lib.cerb_bbox_decode_fwd.argtypes = [vp, vp, lg, i, i, i, vp, vp]
+    lib.cerb_bbox_decode_bwd.restype = i
+    lib.cerb_bbox_decode_bwd.argtypes = [vp, vp, lg, i, i, vp, vp]
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
     lib.cerb_debug_set_hist_sample.restype = i

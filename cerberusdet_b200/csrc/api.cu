@@ -300,3 +300,37 @@ extern "C" int cerb_val_match(const float* dets, const int* counts, int B, int m
     }
     return 0;
 }
+
+// ------------------------------------------------------------------ training-time sibling decode
+extern "C" int cerb_bbox_decode_fwd(const void* pred_dist, const void* anchor_points, long n_rows, int A, int reg_max,
+                                    int dtype, void* out, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(dtype == CERB_F16 || dtype == CERB_F32, "cerb_bbox_decode_fwd: unsupported dtype %d", dtype);
+    REQUIRE(reg_max == CERB_REG_MAX, "cerb_bbox_decode_fwd: reg_max=%d, only %d is supported (models/yolo.py:75)", reg_max, CERB_REG_MAX);
+    REQUIRE(n_rows >= 0 && n_rows < (1l << 40) && A >= 0, "cerb_bbox_decode_fwd: bad sizes n_rows=%ld A=%d", n_rows, A);
+    if (n_rows == 0) return 0;
+    REQUIRE(A >= 1 && n_rows % A == 0, "cerb_bbox_decode_fwd: n_rows=%ld is not a multiple of A=%d", n_rows, A);
+    REQUIRE(pred_dist && anchor_points && out, "cerb_bbox_decode_fwd: null argument");
+    cudaError_t e = cerb_launch_bbox_decode_fwd(pred_dist, anchor_points, n_rows, A, dtype, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_bbox_decode_fwd: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}
+
+extern "C" int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_rows, int reg_max, int dtype,
+                                    void* grad_pred_dist, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(dtype == CERB_F16 || dtype == CERB_F32, "cerb_bbox_decode_bwd: unsupported dtype %d", dtype);
+    REQUIRE(reg_max == CERB_REG_MAX, "cerb_bbox_decode_bwd: reg_max=%d, only %d is supported (models/yolo.py:75)", reg_max, CERB_REG_MAX);
+    REQUIRE(n_rows >= 0 && n_rows < (1l << 40), "cerb_bbox_decode_bwd: bad n_rows=%ld", n_rows);
+    if (n_rows == 0) return 0;
+    REQUIRE(pred_dist && grad_out && grad_pred_dist, "cerb_bbox_decode_bwd: null argument");
+    cudaError_t e = cerb_launch_bbox_decode_bwd(pred_dist, grad_out, n_rows, dtype, grad_pred_dist, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_bbox_decode_bwd: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}

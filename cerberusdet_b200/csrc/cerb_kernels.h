@@ -77,3 +77,10 @@ struct ValMatchParams {
     unsigned char* correct;     // [B, max_det, K]
 };
 cudaError_t cerb_launch_val_match(const ValMatchParams& P, int max_labels_per_image, cudaStream_t stream);
+
+// ------------------------------------------------------------------ training-time sibling decode
+// Loss.bbox_decode forward / backward on pred_dist [n_rows = B * A, 64] (bins contiguous); train_decode.cu
+cudaError_t cerb_launch_bbox_decode_fwd(const void* pred, const void* anchor_points, long n_rows, int A, int dtype, void* out,
+                                        cudaStream_t stream);
+cudaError_t cerb_launch_bbox_decode_bwd(const void* pred, const void* grad_out, long n_rows, int dtype, void* grad_in,
+                                        cudaStream_t stream);

@@ -348,3 +348,48 @@ def match_batch(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, 
                                 offs_d.data_ptr(), mmax, _lib.float_array(iou_host), K, correct.data_ptr(), _stream_ptr(dev))
     _lib.check(rc)
     return correct.bool()
+
+
+# ----------------------------------------------------------------------------- training-time sibling decode
+class _BboxDecode(torch.autograd.Function):
+    """``Loss.bbox_decode`` (reference utils/loss.py:126-131) as one CUDA kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        _require_cuda(pred_dist, "pred_dist")
+        if pred_dist.dim() != 3 or pred_dist.shape[2] != 64:
+            raise ValueError(f"pred_dist must be [B, A, 64] (reg_max 16), got {tuple(pred_dist.shape)}")
+        B, A, _ = pred_dist.shape
+        if tuple(anchor_points.shape) != (A, 2):
+            raise ValueError(f"anchor_points must be [{A}, 2], got {tuple(anchor_points.shape)}")
+        if anchor_points.device != pred_dist.device:
+            raise TypeError("anchor_points and pred_dist must be on the same device")
+        code = _dtype_code(pred_dist)
+        x = pred_dist.contiguous()
+        ap = anchor_points.to(pred_dist.dtype).contiguous()
+        out = torch.empty((B, A, 4), dtype=pred_dist.dtype, device=pred_dist.device)
+        with torch.cuda.device(x.device):
+            rc = lib.cerb_bbox_decode_fwd(x.data_ptr(), ap.data_ptr(), B * A, A, 16, code, out.data_ptr(), _stream_ptr(x.device))
+        _lib.check(rc)
+        ctx.save_for_backward(x)
+        ctx.code = code
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        (x,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = grad_out.to(x.dtype).contiguous()
+        grad_in = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = lib.cerb_bbox_decode_bwd(x.data_ptr(), g.data_ptr(), x.shape[0] * x.shape[1], 16, ctx.code,
+                                          grad_in.data_ptr(), _stream_ptr(x.device))
+        _lib.check(rc)
+        return None, grad_in
+
+
+def bbox_decode(anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> torch.Tensor:
+    """Drop-in for the reference's ``Loss.bbox_decode(anchor_points, pred_dist)`` with ``use_dfl`` (utils/loss.py:126-131):
+    ``pred_dist [B, A, 64]`` -> ``[B, A, 4]`` (x1, y1, x2, y2) in grid units, differentiable w.r.t. ``pred_dist``."""
+    return _BboxDecode.apply(anchor_points, pred_dist)

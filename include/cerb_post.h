@@ -147,6 +147,28 @@ int cerb_val_match(const float* dets, const int* counts, int B, int max_det, con
                    unsigned char* correct, void* stream);
 
 /*
+ * Training-time sibling of the decode: Loss.bbox_decode (cerberusdet/utils/loss.py:126-131) =
+ * softmax over the reg_max bins of each side, expectation with proj = arange(reg_max), then
+ * dist2bbox(xywh=False) (cerberusdet/utils/tal.py:196-205).
+ *
+ *   pred_dist       [n_rows, 4 * reg_max], n_rows = B * A, the bins of a side contiguous (loss.py:139-146), fp16 | fp32
+ *   anchor_points   [A, 2] (x, y) in grid units, same dtype (make_anchors, tal.py:181-193)
+ *   out             [n_rows, 4] = (x1, y1, x2, y2) in grid units, same dtype
+ * reg_max must be 16 (models/yolo.py:75).  Half tensors round where the reference's do (softmax output, the
+ * expectation, the corner).
+ */
+int cerb_bbox_decode_fwd(const void* pred_dist, const void* anchor_points, long n_rows, int A, int reg_max, int dtype,
+                         void* out, void* stream);
+
+/*
+ * Its backward: grad_pred_dist [n_rows, 4 * reg_max] from grad_out [n_rows, 4] -- the fused autograd of
+ * dist2bbox (sign), matmul (g * k, rounded in the tensor dtype) and softmax (p_j * (gp_j - sum_k gp_k p_k));
+ * the probabilities are recomputed from pred_dist.
+ */
+int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_rows, int reg_max, int dtype,
+                         void* grad_pred_dist, void* stream);
+
+/*
  * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy
  * top-k so small inputs exercise the multi-chunk and radix-refinement paths.
  * (0, 0) restores the defaults.  Results never depend on these values.

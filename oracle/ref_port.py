@@ -233,3 +233,15 @@ def postprocess_port(task_levels, ncs, strides, **nms_kw):
         y = decode_port(levels, nc, strides)
         results.append(nms_port(y, **nms_kw))
     return results
+
+
+# --------------------------------------------------------------------------- training-time sibling decode
+def bbox_decode_port(anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> torch.Tensor:
+    """``Loss.bbox_decode`` with ``use_dfl`` (utils/loss.py:126-131) followed by ``dist2bbox(xywh=False)``
+    (utils/tal.py:196-205): ``pred_dist [B, A, 64]`` (bins of a side contiguous) and ``anchor_points [A, 2]`` ->
+    ``[B, A, 4]`` = (x1, y1, x2, y2) in grid units.  Differentiable (the test compares autograd gradients too)."""
+    b, a, c = pred_dist.shape
+    proj = torch.arange(REG_MAX, dtype=torch.float)
+    dist = pred_dist.view(b, a, 4, c // 4).softmax(3).matmul(proj.type(pred_dist.dtype))
+    lt, rb = torch.split(dist, 2, -1)
+    return torch.cat((anchor_points - lt, anchor_points + rb), -1)

@@ -6,7 +6,7 @@ import torch
 
 from conftest import golden_manifest, golden_names, load_golden, split_rows
 from cerberusdet_b200.synth import STRIDES, level_shapes, synth_heads, synth_prediction
-from tol import check_decode
+from tol import check_bbox_decode, check_decode
 
 pytestmark = pytest.mark.gpu
 
@@ -414,3 +414,76 @@ def test_real_model_config1_vectors_gpu(ops, name):
     assert ok, msg
     got = non_max_suppression(_dev(ref_y), **meta["kwargs"])
     _assert_rows_equal(got, split_rows(g["rows"], g["counts"]), name)
+
+
+# ------------------------------------------------------------------ training-time sibling decode
+@pytest.mark.parametrize("name", golden_names("train_bbox"))
+def test_bbox_decode_golden_forward_and_backward(ops, name):
+    """Loss.bbox_decode (reference utils/loss.py:126-131) through the C ABI against vectors from the unmodified reference."""
+    g = load_golden(name)
+    ap = _dev(torch.from_numpy(g["anchor_points"]))
+    pred = _dev(torch.from_numpy(g["pred"])).requires_grad_(True)
+    out = ops.bbox_decode(ap, pred)
+    ref = torch.from_numpy(g["out"])
+    assert out.dtype == ref.dtype and tuple(out.shape) == tuple(ref.shape)
+    ok, msg = check_bbox_decode(out.detach(), ref, gmax=float(g["anchor_points"].max()) + 16.0)
+    assert ok, "forward: " + msg
+    go = torch.from_numpy(g["grad_out"])
+    (gi,) = torch.autograd.grad(out, pred, _dev(go))
+    ok, msg = check_bbox_decode(gi, torch.from_numpy(g["grad_in"]), grad=True, grad_out=go)
+    assert ok, "backward: " + msg
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("bsz,imgsz,scale", [(16, 640, 3.0), (2, 1280, 8.0), (1, 64, 20.0)])
+def test_bbox_decode_vs_oracle(ops, dtype, bsz, imgsz, scale):
+    """Seeded logits at BASELINE sizes (8400 / 33600 anchors) against the oracle port and its autograd gradient;
+    also the unaligned (storage offset) path and linearity of the backward in grad_out."""
+    from oracle import ref_port as rp
+
+    shapes = level_shapes((imgsz, imgsz), STRIDES)
+    anchors, _ = rp.anchor_grid(shapes, STRIDES, dtype)
+    ap = anchors.transpose(0, 1).contiguous()  # [A, 2]
+    A = ap.shape[0]
+    gen = torch.Generator().manual_seed(1000 + imgsz + bsz)
+    pred = (torch.randn(bsz, A, 64, generator=gen) * scale).to(dtype)
+    go = torch.randn(bsz, A, 4, generator=gen).to(dtype)
+    p_ref = pred.clone().requires_grad_(True)
+    want = rp.bbox_decode_port(ap, p_ref)
+    (want_g,) = torch.autograd.grad(want, p_ref, go)
+
+    p_dev = _dev(pred).requires_grad_(True)
+    out = ops.bbox_decode(_dev(ap), p_dev)
+    ok, msg = check_bbox_decode(out.detach(), want.detach(), gmax=float(ap.max()) + 16.0)
+    assert ok, "forward: " + msg
+    (gi,) = torch.autograd.grad(out, p_dev, _dev(go))
+    ok, msg = check_bbox_decode(gi, want_g, grad=True, grad_out=go)
+    assert ok, "backward: " + msg
+
+    # a contiguous view at an odd element offset takes the scalar-load path: same bits
+    buf = torch.empty(pred.numel() + 1, dtype=dtype, device="cuda")
+    view = buf[1:].view(bsz, A, 64)
+    view.copy_(pred)
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    v = view.detach().requires_grad_(True)
+    out2 = ops.bbox_decode(_dev(ap), v)
+    assert torch.equal(out2, out)
+    (gi2,) = torch.autograd.grad(out2, v, _dev(go))
+    assert torch.equal(gi2, gi)
+
+    if dtype == torch.float32:  # backward is linear in grad_out: doubling it doubles every (normal) gradient exactly
+        p3 = _dev(pred).requires_grad_(True)
+        (gi3,) = torch.autograd.grad(ops.bbox_decode(_dev(ap), p3), p3, _dev(go) * 2)
+        assert ((gi3 - gi * 2).abs() <= 1e-38).all()  # exact, except that subnormal results lose bits
+
+
+def test_bbox_decode_rejects_bad_arguments(ops):
+    ap = torch.zeros(10, 2)
+    with pytest.raises(TypeError):
+        ops.bbox_decode(ap, torch.zeros(1, 10, 64))  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        ops.bbox_decode(ap.cuda(), torch.zeros(1, 10, 32, device="cuda"))  # reg_max != 16
+    with pytest.raises(ValueError):
+        ops.bbox_decode(ap.cuda(), torch.zeros(1, 11, 64, device="cuda"))  # anchor count mismatch
+    out = ops.bbox_decode(torch.zeros(0, 2, device="cuda"), torch.zeros(2, 0, 64, device="cuda"))
+    assert tuple(out.shape) == (2, 0, 4)

@@ -83,3 +83,18 @@ def test_real_model_config1_vectors(name):
         got = rp.nms_port(y, greedy=greedy, **meta["kwargs"])
         want = split_rows(g["rows"], g["counts"])
         assert len(got) == 1 and torch.equal(got[0], want[0])
+
+
+# ------------------------------------------------------------------ training-time sibling decode
+@pytest.mark.parametrize("name", golden_names("train_bbox"))
+def test_bbox_decode_port_bit_exact(name):
+    """The oracle restatement of Loss.bbox_decode (utils/loss.py:126-131) against vectors the unmodified reference
+    produced (oracle/gen_golden_train.py): forward and the autograd gradient, bit for bit (same ATen kernels)."""
+    from oracle import ref_port as rp
+
+    g = load_golden(name)
+    pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+    out = rp.bbox_decode_port(torch.from_numpy(g["anchor_points"]), pred)
+    assert torch.equal(out.detach(), torch.from_numpy(g["out"]))
+    (grad_in,) = torch.autograd.grad(out, pred, torch.from_numpy(g["grad_out"]))
+    assert torch.equal(grad_in, torch.from_numpy(g["grad_in"]))

@@ -56,3 +56,30 @@ def check_decode(y, ref, level_hw, strides, nc):
         if nbox > 0.02 * ref[:, :4].numel() + 8 or ncls > 0.01 * ref[:, 4:].numel() + 8:
             return False, f"too many 1-ulp flips: box {nbox}/{ref[:, :4].numel()}, scores {ncls}/{ref[:, 4:].numel()}"
     return True, "ok"
+
+
+def check_bbox_decode(out, ref, grad=False, grad_out=None, gmax=None):
+    """Training-time decode (Loss.bbox_decode).  Forward: a corner is ``anchor -/+ distance`` (grid units), so like
+    the inference boxes its absolute error is a few ulps of the OPERANDS (``gmax`` = largest anchor coordinate + 16),
+    however small the corner itself is: the north_star's relative bound plus 1 ulp(gmax) in fp16 / 4 ulp(gmax) in fp32.
+    Backward (``grad=True``): the gradient of a bin is ``p_j * (g*j - g*d)`` -- a difference of terms of size
+    ``16 |g|`` -- so the absolute term scales with the incoming gradient of that side: ``rtol * 16 * |g|``."""
+    dtype = ref.dtype
+    rtol = 1e-3 if dtype == torch.float16 else 1e-5
+    of, rf = out.float().cpu(), ref.float().cpu()
+    if not torch.isfinite(of).all():
+        return False, "non-finite output"
+    if not grad:
+        atol = 1.0 * _ulp(gmax, 10) if dtype == torch.float16 else 4.0 * _ulp(gmax, 23)
+        bound = rtol * rf.abs() + atol
+    else:
+        g = grad_out.float().cpu().abs()  # [B, A, 4] -> per side, broadcast over its 16 bins
+        bound = rtol * rf.abs() + rtol * 16.0 * g.repeat_interleave(16, dim=-1) + (1e-7 if dtype == torch.float16 else 1e-12)
+    d = (of - rf).abs()
+    if (d > bound).any():
+        return False, f"mismatch: worst excess {(d - bound).max().item():.3e} at flat {(d - bound).argmax().item()}"
+    if dtype == torch.float16:
+        n = (out.cpu() != ref.cpu()).sum().item()
+        if n > 0.02 * ref.numel() + 8:
+            return False, f"too many 1-ulp flips: {n}/{ref.numel()}"
+    return True, "ok"
