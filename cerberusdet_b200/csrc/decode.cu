@@ -20,6 +20,9 @@
 template <typename T, int VEC>
 __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __grid_constant__ DecodeParams P) {
     // ---- block -> (row, part, vector block); uniform per block
+    // the next kernel in the stream (NMS, launched with programmatic stream serialization) may be scheduled as this
+    // grid drains; it waits for this grid's completion (griddepcontrol.wait) before it reads y
+    asm volatile("griddepcontrol.launch_dependents;");
     int row = 0;
     {
         int lo = 0, hi = P.nrows;  // row_start[lo] <= blockIdx.x < row_start[hi]

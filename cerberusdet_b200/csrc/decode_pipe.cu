@@ -48,6 +48,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 template <typename T, int VEC, int IPT>
 __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(const __grid_constant__ PipeParams Q) {
     static_assert(sizeof(T) * VEC == 16, "the pipelined kernel moves 16-byte vectors");
+    // the next kernel in the stream (NMS, launched with programmatic stream serialization) may be scheduled as this
+    // grid drains; it waits for this grid's completion (griddepcontrol.wait) before it reads y
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ uint4 pipe_smem[];  // [PIPE_SLOT_VECS][DEC_THREADS]: conflict-free for 128-bit accesses
     const DecodeParams& P = Q.d;
     uint4* const my = pipe_smem + threadIdx.x;

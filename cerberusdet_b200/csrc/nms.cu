@@ -34,6 +34,8 @@
 //    separately rounded fp32 ops on class-offset boxes, strict '>' against the threshold
 //    (the double-precision compare is folded into iou_thr).
 //  History, counters and the experiments that did not work: profiles/r01_nms.md.
+#include <stdlib.h>
+
 #include "cerb_kernels.h"
 
 #define NMS_THREADS 512
@@ -718,6 +720,9 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
         suffix_scan(S.g0, S.warp_tot);
     };
     PROF(0);  // setup
+    // Programmatic dependent launch: this grid may have been started while the kernel before it in the stream (the
+    // decode kernel) was still draining; nothing above touched global memory.  Wait for that kernel's results here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (smax) build_hist_summary(); else build_hist(hstride, NMS_BINS);
     PROF(1);  // first histogram
 
@@ -1060,8 +1065,21 @@ template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParam
     const size_t smem = sizeof(NmsSmem);
     cudaError_t e = cudaFuncSetAttribute(nms_kernel<T, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    nms_kernel<T, MULTI><<<P.T * P.B, NMS_THREADS, smem, stream>>>(P);
-    return cudaGetLastError();
+    // launched with programmatic stream serialization: the CTAs may be scheduled as soon as every CTA of the previous
+    // kernel has started (the decode kernels signal launch_dependents at entry) and block in griddepcontrol.wait until
+    // it has completed -- hides the launch latency and the prologue behind the decode kernel's tail
+    static const bool pdl = getenv("CERB_DEBUG_NO_PDL") == nullptr;  // tools/ only
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(P.T * P.B));
+    cfg.blockDim = dim3(NMS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, nms_kernel<T, MULTI>, P);
 }
 
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream) {

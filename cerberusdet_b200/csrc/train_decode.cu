@@ -5,7 +5,7 @@
 //     dist2bbox(pred_dist, anchor_points, xywh=False)              utils/tal.py:196-205 -> (x1, y1, x2, y2), grid units
 // The layout differs from the inference path: pred_dist is [B, A, 64], the 16 bins of a side are contiguous
 // (loss.py:139-146 permutes the raw heads), so a thread owns one (anchor, side): 16 contiguous values in
-// (2 or 4 128-bit loads, a warp reads 1 or 2 KB contiguous), one value out.  Same rounding points as the
+// (1 or 2 256-bit loads, a warp reads 1 KB contiguous per instruction), one value out.  Same rounding points as the
 // inference kernel for half tensors (dfl_expectation<T>): probabilities rounded to half, fp32 accumulation
 // rounded once, the corner rounded once.
 //
@@ -18,16 +18,32 @@
 
 #define TD_THREADS 256
 
+// 256-bit global accesses (sm_100a: LDG.E.256 / STG.E.256): a thread's 16 half bins are exactly one 32-byte sector, so
+// a warp reads 1 KB contiguous per instruction with every sector requested once
+struct __align__(32) U8x32 { uint32_t w[8]; };
+__device__ __forceinline__ U8x32 ldg_stream32(const void* p) {
+    U8x32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream32(void* p, const U8x32& r) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]),
+                 "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+                 : "memory");
+}
+
 template <typename T> struct Row16;  // the 16 bins of one (anchor, side)
 template <> struct Row16<__half> {
-    static constexpr int NV = 2;
-    uint4 v[2];
+    static constexpr int NV = 1;
+    U8x32 v[1];
     __device__ __forceinline__ float get(int k) const { return __half2float(reinterpret_cast<const __half*>(v)[k]); }
     __device__ __forceinline__ void set(int k, float f) { reinterpret_cast<__half*>(v)[k] = from_f32<__half>(f); }
 };
 template <> struct Row16<float> {
-    static constexpr int NV = 4;
-    uint4 v[4];
+    static constexpr int NV = 2;
+    U8x32 v[2];
     __device__ __forceinline__ float get(int k) const { return reinterpret_cast<const float*>(v)[k]; }
     __device__ __forceinline__ void set(int k, float f) { reinterpret_cast<float*>(v)[k] = f; }
 };
@@ -35,7 +51,7 @@ template <> struct Row16<float> {
 template <typename T, bool ALIGNED> __device__ __forceinline__ void load_row(const T* p, Row16<T>& r) {
     if constexpr (ALIGNED) {
 #pragma unroll
-        for (int i = 0; i < Row16<T>::NV; ++i) r.v[i] = ldg_stream16(reinterpret_cast<const uint4*>(p) + i);
+        for (int i = 0; i < Row16<T>::NV; ++i) r.v[i] = ldg_stream32(reinterpret_cast<const U8x32*>(p) + i);
     } else {
 #pragma unroll
         for (int k = 0; k < CERB_REG_MAX; ++k) reinterpret_cast<T*>(r.v)[k] = p[k];
@@ -44,7 +60,7 @@ template <typename T, bool ALIGNED> __device__ __forceinline__ void load_row(con
 template <typename T, bool ALIGNED> __device__ __forceinline__ void store_row(T* p, const Row16<T>& r) {
     if constexpr (ALIGNED) {
 #pragma unroll
-        for (int i = 0; i < Row16<T>::NV; ++i) stg_stream16(reinterpret_cast<uint4*>(p) + i, r.v[i]);
+        for (int i = 0; i < Row16<T>::NV; ++i) stg_stream32(reinterpret_cast<U8x32*>(p) + i, r.v[i]);
     } else {
 #pragma unroll
         for (int k = 0; k < CERB_REG_MAX; ++k) p[k] = reinterpret_cast<const T*>(r.v)[k];
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__(TD_THREADS) bbox_decode_bwd_kernel(const T* __
     store_row<T, ALIGNED>(grad_in + idx * CERB_REG_MAX, r);
 }
 
-static bool td_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool td_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 
 cudaError_t cerb_launch_bbox_decode_fwd(const void* pred, const void* anchor_points, long n_rows, int A, int dtype, void* out,
                                         cudaStream_t stream) {

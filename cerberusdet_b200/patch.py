@@ -7,7 +7,9 @@ What gets rebound (and restored by ``uninstall()``):
 * the name ``non_max_suppression`` in ``cerberusdet.utils.general`` and in every module that imported it
   by name at import time (``val``, ``detect``, ``cerberusdet_inference`` -- reference val.py:17,
   detect.py:18, cerberusdet_inference.py:10);
-* ``cerberusdet.cerberusdet_inference.CerberusDetInference`` -> ``inference.CerberusDetInference``.
+* ``cerberusdet.cerberusdet_inference.CerberusDetInference`` -> ``inference.CerberusDetInference``;
+* with ``train=True`` also ``cerberusdet.utils.loss.Loss.bbox_decode`` -> ``ops.bbox_decode`` (the training-time
+  sibling of the decode, reference utils/loss.py:126-131; forward and backward kernels).
 
 CUDA fp16/fp32 tensors go to the kernels; anything else (CPU tensors, training mode, masks/labels
 arguments) is handed to the reference's own, saved implementation -- the patch never changes what a
@@ -32,10 +34,11 @@ def installed() -> bool:
     return bool(_saved)
 
 
-def install(import_all: bool = False) -> Dict[str, List[str]]:
+def install(import_all: bool = False, train: bool = False) -> Dict[str, List[str]]:
     """Patch the reference modules that are importable.  ``import_all`` also imports ``val`` /
     ``detect`` / ``cerberusdet_inference`` (they pull in the whole data pipeline); by default only
-    modules already imported, plus ``models.yolo`` and ``utils.general``, are touched."""
+    modules already imported, plus ``models.yolo`` and ``utils.general``, are touched.  ``train`` also rebinds
+    ``Loss.bbox_decode`` (imports ``cerberusdet.utils.loss``)."""
     if _saved:
         return {"already": ["installed"]}
     import torch
@@ -80,6 +83,22 @@ def install(import_all: bool = False) -> Dict[str, List[str]]:
     if inf is not None:
         _set(inf, "CerberusDetInference", _inference.CerberusDetInference)
         done["patched"].append("cerberusdet.cerberusdet_inference.CerberusDetInference")
+    if train:
+        from . import ops as _ops
+
+        loss_mod = importlib.import_module("cerberusdet.utils.loss")
+        reference_bbox_decode = loss_mod.Loss.bbox_decode
+
+        def bbox_decode(self, anchor_points, pred_dist):
+            on_path = (self.use_dfl and pred_dist.is_cuda and pred_dist.dtype in (torch.float16, torch.float32)
+                       and pred_dist.dim() == 3 and pred_dist.shape[-1] == 64 and not torch.is_autocast_enabled())
+            if not on_path:  # CPU tensors, reg_max != 16, autocast (its softmax/matmul casts are the reference's business)
+                return reference_bbox_decode(self, anchor_points, pred_dist)
+            return _ops.bbox_decode(anchor_points, pred_dist)
+
+        bbox_decode._cerb_reference = reference_bbox_decode
+        _set(loss_mod.Loss, "bbox_decode", bbox_decode)
+        done["patched"].append("cerberusdet.utils.loss.Loss.bbox_decode")
     return done
 
 

@@ -173,6 +173,28 @@ def test_patch_install_rebinds_and_restores():
     assert ref.yolo.Detect.forward is orig_fwd and ref.general.non_max_suppression is orig_nms
 
 
+@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+def test_patch_install_train_rebinds_bbox_decode_and_keeps_cpu_results():
+    import types
+
+    from cerberusdet_b200 import patch
+    from oracle.ref_import import load_reference
+
+    load_reference()
+    import cerberusdet.utils.loss as loss_mod
+
+    orig = loss_mod.Loss.bbox_decode
+    info = patch.install(train=True)
+    try:
+        assert "cerberusdet.utils.loss.Loss.bbox_decode" in info["patched"] and loss_mod.Loss.bbox_decode is not orig
+        me = types.SimpleNamespace(use_dfl=True, proj=torch.arange(16, dtype=torch.float))
+        ap, pred = torch.rand(30, 2) * 8, torch.randn(2, 30, 64)
+        assert torch.equal(loss_mod.Loss.bbox_decode(me, ap, pred), orig(me, ap, pred))  # CPU: the reference's own code
+    finally:
+        patch.uninstall()
+    assert loss_mod.Loss.bbox_decode is orig
+
+
 _WORKER2 = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
