@@ -18,6 +18,7 @@ EXPORTS = (
     "cerb_version",
     "cerb_last_error",
     "cerb_decode",
+    "cerb_decode_split",
     "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
@@ -56,6 +57,8 @@ def load() -> ctypes.CDLL:
     lib.cerb_last_error.argtypes = []
     lib.cerb_decode.restype = i
     lib.cerb_decode.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
+    lib.cerb_decode_split.restype = i
+    lib.cerb_decode_split.argtypes = [vpp, vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
     lib.cerb_summary_row_len.restype = sz
     lib.cerb_summary_row_len.argtypes = [i, i]
     lib.cerb_nms_workspace_bytes.restype = sz

@@ -61,9 +61,9 @@ extern "C" size_t cerb_summary_row_len(int A, int dtype) {
     return ((size_t)A / V + V - 1) / V * V;
 }
 
-extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
-                           const float* strides, int dtype, void* const* y, void* const* smax, int* summary_written,
-                           void* stream) {
+static int decode_common(const void* const* lvl, const void* const* cls_lvl, const int* nc, int T, int L, int B,
+                         const int* H, const int* W, const float* strides, int dtype, void* const* y, void* const* smax,
+                         int* summary_written, void* stream) {
     g_err[0] = 0;
     REQUIRE(lvl && nc && H && W && strides && y, "cerb_decode: null argument");
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_decode: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
@@ -100,6 +100,12 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
             REQUIRE(p != nullptr || B == 0, "cerb_decode: lvl[%d][%d] is null", t, l);
             P.lvl[t][l] = p;
             while (vec > 1 && !aligned_to(p, vec * elt)) vec >>= 1;
+            if (cls_lvl != nullptr) {
+                const void* c = cls_lvl[t * L + l];
+                REQUIRE(c != nullptr || B == 0, "cerb_decode_split: cls_lvl[%d][%d] is null", t, l);
+                P.cls[t][l] = c;
+                while (vec > 1 && !aligned_to(c, vec * elt)) vec >>= 1;
+            }
         }
     }
     if (const char* ev = getenv("CERB_DEBUG_DECODE_VEC")) { int v = atoi(ev); if (v >= 1 && v < vec) vec = v; }  // tools/ only
@@ -117,7 +123,7 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
     // The TMA-pipelined kernel (decode_tma.cu) is kept as a measured alternative; the register-resident kernel is
     // faster on B200 for both dtypes (profiles/r01_decode.md), so it is the default.
     bool use_tma = false;
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = vec == (int)(16 / elt) && atoi(ev) != 0;  // tools/ only
+    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = cls_lvl == nullptr && vec == (int)(16 / elt) && atoi(ev) != 0;  // tools/ only
     if (use_tma) e = cerb_launch_decode_tma(P, dtype, (cudaStream_t)stream);
     // software-pipelined kernel (decode_pipe.cu): items per thread, 0 = the register-resident kernel
     int pipe_ipt = CERB_DECODE_PIPE_DEFAULT(dtype);
@@ -132,6 +138,22 @@ extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, 
         return CERB_ECUDA;
     }
     return 0;
+}
+
+extern "C" int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,
+                           const float* strides, int dtype, void* const* y, void* const* smax, int* summary_written,
+                           void* stream) {
+    return decode_common(lvl, nullptr, nc, T, L, B, H, W, strides, dtype, y, smax, summary_written, stream);
+}
+
+extern "C" int cerb_decode_split(const void* const* box_lvl, const void* const* cls_lvl, const int* nc, int T, int L, int B,
+                                 const int* H, const int* W, const float* strides, int dtype, void* const* y,
+                                 void* const* smax, int* summary_written, void* stream) {
+    if (cls_lvl == nullptr) {
+        cerb_set_error("cerb_decode_split: null argument");
+        return CERB_EINVAL;
+    }
+    return decode_common(box_lvl, cls_lvl, nc, T, L, B, H, W, strides, dtype, y, smax, summary_written, stream);
 }
 
 extern "C" size_t cerb_nms_workspace_bytes(int T, int B, int max_det) {

@@ -6,6 +6,10 @@
 // ------------------------------------------------------------------ decode
 struct DecodeParams {
     const void* lvl[CERB_MAX_TASKS][CERB_MAX_LEVELS];  // raw head tensors [B, 64+nc, H_l, W_l]
+    // optional split heads: class channels [B, nc, H_l, W_l] of each (task, level) in their own tensor (the cv3 tower's
+    // output) and lvl = the box channels [B, 64, H_l, W_l] alone (cv2's output) -- the reference's channel concat
+    // (models/yolo.py:90) is then never materialised.  null = lvl holds both, concatenated
+    const void* cls[CERB_MAX_TASKS][CERB_MAX_LEVELS];
     void* y[CERB_MAX_TASKS];                           // decoded [B, 4+nc, A]
     int nc[CERB_MAX_TASKS];
     int hw[CERB_MAX_LEVELS];

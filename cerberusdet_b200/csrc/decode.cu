@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
 
     const int nc = P.nc[task];
     const int no = 4 * CERB_REG_MAX + nc;
-    const T* __restrict__ in = reinterpret_cast<const T*>(P.lvl[task][level]) + (size_t)b * no * hw + a0;
+    const T* __restrict__ clsp = reinterpret_cast<const T*>(P.cls[task][level]);  // split heads, or null
+    const T* __restrict__ in = reinterpret_cast<const T*>(P.lvl[task][level]) +
+                               (size_t)b * (clsp ? 4 * CERB_REG_MAX : no) * hw + a0;
     T* __restrict__ out = reinterpret_cast<T*>(P.y[task]) + (size_t)b * (4 + nc) * P.A + P.aoff[level] + a0;
 
     if (part < 2) {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
         // kernel read only the vectors that can hold a candidate.
         const int c0 = (part - 2) * CLS_CHUNK;
         const int c1 = min(nc, c0 + CLS_CHUNK);
-        const T* __restrict__ cin = in + (size_t)(4 * CERB_REG_MAX) * hw;
+        const T* __restrict__ cin = clsp ? clsp + (size_t)b * nc * hw + a0 : in + (size_t)(4 * CERB_REG_MAX) * hw;
         T* __restrict__ cout = out + (size_t)4 * P.A;
         T* __restrict__ smax = nullptr;  // [B, nc, srow], srow = roundup(A / VEC, VEC)
         const size_t srow = ((size_t)(P.A / VEC) + VEC - 1) / VEC * VEC;

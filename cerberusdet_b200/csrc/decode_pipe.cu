@@ -78,8 +78,12 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
     const int cnt = min(IPT, (n_items - first + DEC_THREADS - 1) / DEC_THREADS);  // my items: first + i * DEC_THREADS
 
     const int nc = P.nc[task];
-    const size_t img_stride = (size_t)(4 * CERB_REG_MAX + nc) * hw;
-    const T* __restrict__ lbase = reinterpret_cast<const T*>(P.lvl[task][level]);
+    // concatenated heads: box and class channels share one tensor; split heads: two tensors (models/yolo.py:90 unmaterialised)
+    const T* __restrict__ clsp = reinterpret_cast<const T*>(P.cls[task][level]);
+    const bool use_cls = kind == 2 && clsp != nullptr;
+    const size_t img_stride = (size_t)(clsp == nullptr ? 4 * CERB_REG_MAX + nc : (kind == 2 ? nc : 4 * CERB_REG_MAX)) * hw;
+    const T* __restrict__ lbase = use_cls ? clsp : reinterpret_cast<const T*>(P.lvl[task][level]);
+    const size_t cls_off = use_cls ? 0 : (size_t)(4 * CERB_REG_MAX) * hw;  // first class channel inside an image
     T* __restrict__ ybase = reinterpret_cast<T*>(P.y[task]) + P.aoff[level];
     const size_t y_img = (size_t)(4 + nc) * P.A;
 
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
         auto class_ptr = [&](int i) -> const T* {
             const int it = first + i * DEC_THREADS;
             const int b = it / nvec, v = it - b * nvec;
-            return lbase + (size_t)b * img_stride + (size_t)(4 * CERB_REG_MAX) * hw + v * VEC;
+            return lbase + (size_t)b * img_stride + cls_off + v * VEC;
         };
         // issue cursor: 4-channel groups in item order; an exhausted cursor still commits (zero-byte) groups so
         // that wait_group<3> always means "the group consumed now has landed"

@@ -24,6 +24,16 @@ def _level_cat(self, x):
     return x
 
 
+class SplitHeads:
+    """Raw heads of one task with the channel concat of models/yolo.py:89-90 left out: ``box[l]`` = cv2[l]'s output
+    ``[B, 64, H_l, W_l]``, ``cls[l]`` = cv3[l]'s ``[B, nc, H_l, W_l]``.  ``ops.decode_heads_split`` reads both."""
+
+    __slots__ = ("box", "cls")
+
+    def __init__(self, box, cls):
+        self.box, self.cls = box, cls
+
+
 def detect_forward(self, x):
     """``forward(self, x: list[Tensor]) -> (y, x)`` | ``y`` (export) | ``x`` (training).
 
@@ -35,9 +45,11 @@ def detect_forward(self, x):
     if self.training or not x[0].is_cuda or x[0].dtype not in (torch.float16, torch.float32):
         return reference_forward(self, x)
     shape = x[0].shape  # BCHW before the convs: the reference's anchor-cache key (yolo.py:88,93)
-    x = _level_cat(self, x)
     if getattr(self, _RAW_FLAG, False):
-        return None, x
+        # inference engine: nobody reads the concatenated raw tensors, so the towers' outputs are handed over as they
+        # are and the decode kernel reads box and class channels from their own tensors (no torch.cat copy)
+        return None, SplitHeads([self.cv2[i](x[i]) for i in range(self.nl)], [self.cv3[i](x[i]) for i in range(self.nl)])
+    x = _level_cat(self, x)
     if self.dynamic or self.shape != shape:
         # keep the instance attributes other code reads (and pickles) populated (yolo.py:93-95)
         from .anchors import make_anchor_tensors

@@ -15,14 +15,14 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import cross_task
-from .detect import _RAW_FLAG
-from .ops import cross_task_merge, decode_heads, nms_batched
+from .detect import _RAW_FLAG, SplitHeads
+from .ops import cross_task_merge, decode_heads, decode_heads_split, nms_batched
 
 
 @contextlib.contextmanager
 def raw_heads(model):
-    """While active, patched Detect heads return ``(None, levels)`` so that all task heads can be
-    decoded together in one launch."""
+    """While active, patched Detect heads return ``(None, SplitHeads)`` -- the conv towers' outputs, not even
+    concatenated -- so that all task heads can be decoded together in one launch."""
     heads = [m for m in model.modules() if hasattr(type(m), "_cerb_reference_forward")]
     for m in heads:
         setattr(m, _RAW_FLAG, True)
@@ -106,7 +106,11 @@ class CerberusDetInference:
         preds = [all_out[t][0] for t in tasks]
         if any(p is None for p in preds):  # raw mode was honoured: decode all heads in one launch
             levels = [all_out[t][1] for t in tasks]
-            preds = decode_heads(levels, self._head_strides(len(levels[0])))
+            if all(isinstance(lv, SplitHeads) for lv in levels):  # patched heads: no channel concat was made
+                strides = self._head_strides(len(levels[0].box))
+                preds = decode_heads_split([lv.box for lv in levels], [lv.cls for lv in levels], strides)
+            else:
+                preds = decode_heads(levels, self._head_strides(len(levels[0])))
         # 2. one NMS launch over all (task, image) segments
         dets, counts = nms_batched(preds, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det)
         bsz = tensor.shape[0]

@@ -36,14 +36,18 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
+def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float],
+                 cls_levels: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """Returns ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``; the score summaries ``smax_t`` are empty
-    tensors when the shapes do not allow them (see include/cerb_post.h)."""
+    tensors when the shapes do not allow them (see include/cerb_post.h).  With ``cls_levels`` the heads are split:
+    ``levels`` hold the 64 box channels, ``cls_levels`` the class channels (``cerb_decode_split``)."""
     lib = _lib.load()
     T = len(nc)
     if T == 0 or len(levels) % T:
         raise ValueError("levels must hold T*L tensors, task-major")
     L = len(levels) // T
+    if cls_levels is not None and len(cls_levels) != len(levels):
+        raise ValueError("cls_levels must hold one tensor per box tensor")
     if len(strides) != L:
         raise ValueError(f"expected {L} strides, got {len(strides)}")
     first = levels[0]
@@ -59,20 +63,32 @@ def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Seq
             x = levels[t * L + l]
             if x.device != first.device or x.dtype != first.dtype:
                 raise TypeError("all head tensors must share device and dtype")
-            if tuple(x.shape) != (B, 64 + nc[t], H[l], W[l]):
-                raise ValueError(f"task {t} level {l}: expected {(B, 64 + nc[t], H[l], W[l])}, got {tuple(x.shape)}")
+            cbox = 64 if cls_levels is not None else 64 + nc[t]
+            if tuple(x.shape) != (B, cbox, H[l], W[l]):
+                raise ValueError(f"task {t} level {l}: expected {(B, cbox, H[l], W[l])}, got {tuple(x.shape)}")
             lv.append(x.contiguous())
+    cl = []
+    if cls_levels is not None:
+        for t in range(T):
+            for l in range(L):
+                c = cls_levels[t * L + l]
+                if c.device != first.device or c.dtype != first.dtype:
+                    raise TypeError("all head tensors must share device and dtype")
+                if tuple(c.shape) != (B, nc[t], H[l], W[l]):
+                    raise ValueError(f"task {t} level {l}: expected class tensor {(B, nc[t], H[l], W[l])}, got {tuple(c.shape)}")
+                cl.append(c.contiguous())
     ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
     R = int(lib.cerb_summary_row_len(A, code))
     sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
     written = ctypes.c_int(0)
+    tail = (_lib.int_array(list(nc)), T, L, B, _lib.int_array(H), _lib.int_array(W),
+            _lib.float_array([float(s) for s in strides]), code, _lib.ptr_array([y.data_ptr() for y in ys]),
+            _lib.ptr_array([x.data_ptr() for x in sm]), ctypes.byref(written), _stream_ptr(first.device))
     with torch.cuda.device(first.device):
-        rc = lib.cerb_decode(
-            _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(list(nc)), T, L, B,
-            _lib.int_array(H), _lib.int_array(W), _lib.float_array([float(s) for s in strides]), code,
-            _lib.ptr_array([y.data_ptr() for y in ys]), _lib.ptr_array([x.data_ptr() for x in sm]),
-            ctypes.byref(written), _stream_ptr(first.device),
-        )
+        if cls_levels is None:
+            rc = lib.cerb_decode(_lib.ptr_array([x.data_ptr() for x in lv]), *tail)
+        else:
+            rc = lib.cerb_decode_split(_lib.ptr_array([x.data_ptr() for x in lv]), _lib.ptr_array([x.data_ptr() for x in cl]), *tail)
     _lib.check(rc)
     if not written.value:
         sm = [y.new_empty((0,)) for y in ys]
@@ -219,6 +235,22 @@ def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequenc
     flat = [x for lv in task_levels for x in lv]
     nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
     out = _decode_impl(flat, nc, [float(s) for s in strides])
+    T = len(nc)
+    ys, sms = out[:T], out[T:]
+    for y, sm in zip(ys, sms):
+        if sm.numel():
+            _remember_summary(y, sm)
+    return ys
+
+
+def decode_heads_split(task_box_levels: Sequence[Sequence[torch.Tensor]], task_cls_levels: Sequence[Sequence[torch.Tensor]],
+                       strides: Sequence[float]) -> List[torch.Tensor]:
+    """``decode_heads`` on SPLIT heads: ``task_box_levels[t][l]`` = ``[B, 64, H_l, W_l]`` (the cv2 tower's output),
+    ``task_cls_levels[t][l]`` = ``[B, nc_t, H_l, W_l]`` (cv3's) -- the reference's channel concat (models/yolo.py:89-90)
+    is never materialised.  Same result, bit for bit, as ``decode_heads`` on the concatenated tensors."""
+    nc = [int(lv[0].shape[1]) for lv in task_cls_levels]
+    out = _decode_impl([x for lv in task_box_levels for x in lv], nc, [float(s) for s in strides],
+                       cls_levels=[x for lv in task_cls_levels for x in lv])
     T = len(nc)
     ys, sms = out[:T], out[T:]
     for y, sm in zip(ys, sms):

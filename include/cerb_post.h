@@ -60,6 +60,21 @@ int cerb_decode(const void* const* lvl, const int* nc, int T, int L, int B, cons
                 void* stream);
 
 /*
+ * The same decode reading SPLIT heads: the box channels and the class channels of every (task, level) stay in the
+ * two tensors the conv towers wrote, so the reference's channel concat
+ * `x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i])), 1)` (cerberusdet/models/yolo.py:89-90, a full copy of
+ * the raw heads) is never materialised.  For callers that do not need the raw `x` Detect.forward returns next to y
+ * (CerberusDetInference.predict drops it, cerberusdet_inference.py:119).
+ *
+ *   box_lvl[t*L + l]  [B, 64, H[l], W[l]]       (cv2[l]'s output)
+ *   cls_lvl[t*L + l]  [B, nc[t], H[l], W[l]]    (cv3[l]'s output)
+ * Everything else as cerb_decode; results are bit-identical to cerb_decode on the concatenated tensors.
+ */
+int cerb_decode_split(const void* const* box_lvl, const void* const* cls_lvl, const int* nc, int T, int L, int B,
+                      const int* H, const int* W, const float* strides, int dtype, void* const* y, void* const* smax,
+                      int* summary_written, void* stream);
+
+/*
  * Score summary (optional by-product of cerb_decode, optional input of cerb_nms).
  *   smax[t]   [B, nc[t], R] in the tensor dtype, R = cerb_summary_row_len(A, dtype): entry (b, c, i) is
  *             the maximum of the 16-byte score vector i of class c, i.e. of the scores of anchors

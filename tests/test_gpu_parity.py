@@ -88,6 +88,35 @@ def test_decode_pipelined_kernel_bit_identical_to_register_kernel(ops, dtype, ip
         assert ok, f"task {t}: {msg}"
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("pipe", ["0", "default"])
+def test_decode_split_heads_bit_identical_to_concatenated(ops, dtype, pipe, monkeypatch):
+    """cerb_decode_split reads the box channels (cv2 output) and the class channels (cv3 output) from their own tensors
+    -- the concat of reference models/yolo.py:89-90 is never made -- and must give the same bits as cerb_decode on the
+    concatenated tensors, through both kernels and on the scalar (unaligned) path."""
+    from cerberusdet_b200 import ops as o
+
+    if pipe != "default":
+        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", pipe)
+    for ncs, imgsz, bsz, strides in [([20, 19, 12], (640, 640), 2, STRIDES), ([80, 3], (96, 72), 3, STRIDES), ([5], (40, 24), 2, (8.0,))]:
+        heads = synth_heads(range(bsz), ncs, imgsz, dtype, "iid", cfg=55, strides=strides)
+        dev = [[_dev(x) for x in lv] for lv in heads]
+        y0 = ops.decode_heads(dev, strides)
+        s0 = [o.find_summary(y) for y in y0]
+        box = [[x[:, :64].contiguous() for x in lv] for lv in dev]
+        cls = [[x[:, 64:].contiguous() for x in lv] for lv in dev]
+        y1 = o.decode_heads_split(box, cls, strides)
+        s1 = [o.find_summary(y) for y in y1]
+        for t in range(len(ncs)):
+            assert torch.equal(y0[t], y1[t]), f"task {t} ncs={ncs} imgsz={imgsz}"
+            assert (s0[t] is None) == (s1[t] is None)
+            if s0[t] is not None:
+                n = y0[t].shape[2] // (8 if dtype == torch.float16 else 4)
+                assert torch.equal(s0[t][..., :n], s1[t][..., :n])
+    with pytest.raises(ValueError):  # class tensor of another spatial shape
+        o.decode_heads_split(box, [[c[:, :, :-1].contiguous() for c in lv] for lv in cls], strides)
+
+
 def test_decode_rejects_cpu_and_bad_shapes(ops):
     heads = synth_heads(range(1), [20], 64, torch.float32)
     with pytest.raises(TypeError):
