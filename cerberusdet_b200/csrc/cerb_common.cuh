@@ -162,9 +162,17 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
     return r;
 }
 __device__ __forceinline__ void stg_stream16(void* p, uint4 v) {
+#ifdef CERB_L2_STORE_HINT  // experiment: keep the decode outputs in L2 for the NMS kernel (profiles/r01_decode.md)
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+#endif
 }
 
 // host-side error plumbing (api.cu)

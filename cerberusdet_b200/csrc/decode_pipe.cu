@@ -37,9 +37,23 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 // src_bytes = 0 reads nothing (the slot is zero-filled): a branch-free "maybe prefetch" that the scheduler
 // cannot sink below the arithmetic the way it sinks a conditional block
+#ifndef CERB_NO_L2_HINTS
+// raw heads are read exactly once: mark their lines evict-first so that y and the score summary (written here, read by
+// the NMS kernel right after) stay in the 126 MB L2 instead of being pushed out by 261 MB of streaming input
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void* src, int src_bytes, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol)
+                 : "memory");
+}
+#else
 __device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -56,6 +70,12 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
     uint4* const my = pipe_smem + threadIdx.x;
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
     constexpr uint32_t SLOT_STRIDE = DEC_THREADS * 16;
+#ifndef CERB_NO_L2_HINTS
+    const uint64_t pol = l2_policy_evict_first();
+#define CERB_POL , pol
+#else
+#define CERB_POL
+#endif
 
     // ---- block -> row; uniform per block
     int row = 0;
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
         };
         auto issue = [&](const T* p, int bytes) {
 #pragma unroll
-            for (int k = 0; k < CERB_REG_MAX; ++k) cp_async16_pred(my_s + k * SLOT_STRIDE, p + (size_t)k * hw, bytes);
+            for (int k = 0; k < CERB_REG_MAX; ++k) cp_async16_pred(my_s + k * SLOT_STRIDE, p + (size_t)k * hw, bytes CERB_POL);
             cp_async_commit();
         };
         issue(side_ptr(0), 16);
@@ -160,7 +180,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = min(ic + u, nc - 1);  // (a valid address either way)
-                cp_async16_pred(my_s + (slot * 4 + u) * SLOT_STRIDE, ip + (size_t)c * hw, (live && ic + u < nc) ? 16 : 0);
+                cp_async16_pred(my_s + (slot * 4 + u) * SLOT_STRIDE, ip + (size_t)c * hw, (live && ic + u < nc) ? 16 : 0 CERB_POL);
             }
             cp_async_commit();
             ic += 4;
