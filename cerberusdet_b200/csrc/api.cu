@@ -119,6 +119,19 @@ static int decode_common(const void* const* lvl, const void* const* cls_lvl, con
             if (summary_written) *summary_written = 1;
         }
     }
+    {
+        // y and the score summary are read by the NMS kernel right after: when they fit in L2 with room to spare, the raw
+        // heads (read once) are streamed with an evict-first policy so that they do not push the outputs out
+        // (profiles/r01_decode.md: fp16 B=64 gains 2 us in decode and 1.4 us in NMS; fp32 B=64, whose outputs do not fit,
+        // loses 7 us with the same hint)
+        size_t out_bytes = 0;
+        for (int t = 0; t < T; ++t)  // y [B, 4+nc, A] + score summary [B, nc, ~A/V]
+            out_bytes += (size_t)B * ((size_t)(4 + nc[t]) * (size_t)P.A + (size_t)nc[t] * ((size_t)P.A / (16 / elt) + 8)) * elt;
+        int dev = 0, l2 = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess)
+            P.l2_evict_first = out_bytes <= (size_t)l2 / 4 * 3;
+        if (const char* ev = getenv("CERB_DEBUG_DECODE_L2HINT")) P.l2_evict_first = atoi(ev);  // tools/ only
+    }
     cudaError_t e = cudaErrorInvalidConfiguration;
     // The TMA-pipelined kernel (decode_tma.cu) is kept as a measured alternative; the register-resident kernel is
     // faster on B200 for both dtypes (profiles/r01_decode.md), so it is the default.

@@ -21,6 +21,7 @@ struct DecodeParams {
     int row_start[2 * CERB_MAX_TASKS * CERB_MAX_LEVELS + 1];    // first block of each row ((task, level), or (kind, task, level) in box-first order)
     int row_blocks_per_part[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // ceil(B * nvecp / threads)
     void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V]: max of every 16-byte score vector
+    int l2_evict_first;          // pipelined kernel: read the raw heads with an L2 evict-first policy (outputs fit in L2)
     int interleave_parts;        // block order: 0 parts contiguous per (task, level), 1 interleaved, 2 all DFL blocks first, then all class blocks
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);

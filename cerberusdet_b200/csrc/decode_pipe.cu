@@ -40,9 +40,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 #ifndef CERB_NO_L2_HINTS
 // raw heads are read exactly once: mark their lines evict-first so that y and the score summary (written here, read by
 // the NMS kernel right after) stay in the 126 MB L2 instead of being pushed out by 261 MB of streaming input
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+// (only when the outputs fit: with fp32 inputs at B=64 -- 152 MB of outputs -- the same hint costs 7 us, so the host
+// decides per launch, DecodeParams::l2_evict_first)
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
     uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void* src, int src_bytes, uint64_t pol) {
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
     constexpr uint32_t SLOT_STRIDE = DEC_THREADS * 16;
 #ifndef CERB_NO_L2_HINTS
-    const uint64_t pol = l2_policy_evict_first();
+    const uint64_t pol = l2_policy(Q.d.l2_evict_first != 0);
 #define CERB_POL , pol
 #else
 #define CERB_POL
