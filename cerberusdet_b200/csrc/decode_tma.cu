@@ -1,5 +1,6 @@
-// Fused Detect-head decode, persistent TMA-pipelined variant (the one the library uses whenever the
-// tensors allow 16-byte rows; decode.cu is the generic fallback and the comparison point).
+// Fused Detect-head decode, persistent TMA-pipelined variant.  OPT-IN (CERB_DEBUG_DECODE_TMA=1, tools/ only): correct,
+// but measured slower on B200 than the cp.async-pipelined kernel in decode_pipe.cu, which is the default
+// (profiles/r01_decode.md has the numbers); kept as the measured alternative.
 //
 // Why: the register-resident kernel in decode.cu is latency bound -- a warp first waits for its 16
 // loads, then spends thousands of cycles on exp/rcp work with nothing in flight, and at ~100-146
