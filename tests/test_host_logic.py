@@ -47,6 +47,17 @@ def test_argument_validation_without_gpu():
     assert lib.cerb_debug_set_chunking(0, 0) == 0
     assert lib.cerb_summary_row_len(8400, 0) == 1056 and lib.cerb_summary_row_len(8400, 1) == 2100
     assert lib.cerb_summary_row_len(8401, 0) == 0
+    # training-time decode: reg_max other than 16 and a row count that is not a multiple of A are refused
+    rc = lib.cerb_bbox_decode_fwd(None, None, 100, 10, 8, 0, None, None)
+    assert rc == _lib.CERB_EINVAL and b"reg_max" in lib.cerb_last_error()
+    rc = lib.cerb_bbox_decode_fwd(None, None, 101, 10, 16, 1, None, None)
+    assert rc == _lib.CERB_EINVAL and b"multiple" in lib.cerb_last_error()
+    assert lib.cerb_bbox_decode_fwd(None, None, 0, 0, 16, 1, None, None) == 0  # empty batch: nothing to launch
+    rc = lib.cerb_bbox_decode_bwd(None, None, 10, 16, 5, None, None)
+    assert rc == _lib.CERB_EINVAL and b"dtype" in lib.cerb_last_error()
+    rc = lib.cerb_decode_split(_lib.ptr_array([0]), None, _lib.int_array([5]), 1, 1, 1, _lib.int_array([2]), _lib.int_array([2]),
+                               _lib.float_array([8.0]), 0, _lib.ptr_array([0]), None, None, None)
+    assert rc == _lib.CERB_EINVAL and b"null" in lib.cerb_last_error()
 
 
 def test_ops_refuse_cpu_tensors():
@@ -59,6 +70,26 @@ def test_ops_refuse_cpu_tensors():
         ops.decode_heads([[torch.zeros(1, 69, 2, 2)]], [8.0])
     with pytest.raises(AssertionError):
         non_max_suppression(torch.zeros(1, 6, 8), conf_thres=2.0)
+    with pytest.raises(TypeError):
+        ops.decode_heads_split([[torch.zeros(1, 64, 2, 2)]], [[torch.zeros(1, 5, 2, 2)]], [8.0])
+    with pytest.raises(TypeError):
+        ops.bbox_decode(torch.zeros(4, 2), torch.zeros(1, 4, 64))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs first) on the host cores: one bounded step, one JSON line."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("BASELINE config 3")
 
 
 def test_shard_ranges_cover_the_batch():
