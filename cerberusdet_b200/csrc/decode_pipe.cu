@@ -263,15 +263,11 @@ template <typename T, int VEC, int IPT> static cudaError_t launch_pipe_t(const D
     q.row_start[r] = blocks;
     if (blocks == 0) return cudaSuccess;
     constexpr size_t smem = (size_t)PIPE_SLOT_VECS * DEC_THREADS * 16;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // per launch, like launch_nms_t: function attributes are per device, and a process may drive several
+    // (32 KB fits the default dynamic limit; the carve-out is what lets 5 CTAs = 165 KB share an SM)
+    cudaError_t e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     decode_pipe_kernel<T, VEC, IPT><<<blocks, DEC_THREADS, smem, stream>>>(q);
     return cudaGetLastError();
 }

@@ -48,6 +48,38 @@
 
 typedef unsigned long long u64;
 
+// Optional per-CTA wall times (-DNMS_BLOCK_TIMES, tools/nms_block_times.py only): start / end %globaltimer and SM id of
+// every CTA of the last launch -- shows whether the kernel's duration is one slow segment or all of them.
+#ifdef NMS_BLOCK_TIMES
+__device__ unsigned long long g_nms_block_t[3][4096];
+__device__ __forceinline__ unsigned long long nms_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+extern "C" int cerb_debug_read_block_times(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    if (n > 4096) n = 4096;
+    for (int k = 0; k < 3; ++k)
+        if (cudaMemcpyFromSymbol(out + (size_t)k * n, g_nms_block_t, sizeof(unsigned long long) * n,
+                                 sizeof(unsigned long long) * 4096 * k) != cudaSuccess)
+            return -1;
+    return 0;
+}
+#define BLOCK_T_START                                                                      \
+    if (threadIdx.x == 0 && blockIdx.x < 4096) {                                            \
+        unsigned smid;                                                                      \
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));                                    \
+        g_nms_block_t[0][blockIdx.x] = nms_globaltimer();                                   \
+        g_nms_block_t[2][blockIdx.x] = smid;                                                \
+    }
+#define BLOCK_T_END \
+    if (threadIdx.x == 0 && blockIdx.x < 4096) g_nms_block_t[1][blockIdx.x] = nms_globaltimer();
+#else
+#define BLOCK_T_START
+#define BLOCK_T_END
+#endif
+
 // Optional phase timers (-DNMS_PROFILE, tools/ only): block 0 accumulates clock64() deltas per phase.
 #ifdef NMS_PROFILE
 __device__ unsigned long long g_nms_prof[16];
@@ -656,6 +688,7 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
+    BLOCK_T_START
     const int seg = blockIdx.x;
     const int task = seg / P.B, b = seg - task * P.B;
     const int nc = P.nc[task], A = P.A;
@@ -1054,6 +1087,7 @@ __global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid
 #ifdef NMS_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0) { g_nms_prof[10] += 1; g_nms_prof[11] += consumed; }
 #endif
+    BLOCK_T_END
 }
 
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
