@@ -680,11 +680,10 @@ template <int E> __device__ __forceinline__ void block_sort_desc(u64* keys) {
     __syncthreads();
 }
 
-#ifndef NMS_MINB
-#define NMS_MINB 2
-#endif
-template <typename T, bool MULTI>
-__global__ void __launch_bounds__(NMS_THREADS, NMS_MINB) nms_kernel(const __grid_constant__ NmsParams P) {
+// MINB = CTAs per SM the registers are budgeted for: 2 (64 registers; needed when there are more segments than SMs) or
+// 1 (128 registers, no spills: 26 % faster per segment, used when every segment gets an SM of its own -- cerb_launch_nms)
+template <typename T, bool MULTI, int MINB>
+__global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
@@ -1095,9 +1094,9 @@ size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {
     return (size_t)T * B * max_det * 5 * sizeof(float);
 }
 
-template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParams& P, cudaStream_t stream) {
+template <typename T, bool MULTI, int MINB> static cudaError_t launch_nms_t(const NmsParams& P, cudaStream_t stream) {
     const size_t smem = sizeof(NmsSmem);
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel<T, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(nms_kernel<T, MULTI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // launched with programmatic stream serialization: the CTAs may be scheduled as soon as every CTA of the previous
     // kernel has started (the decode kernels signal launch_dependents at entry) and block in griddepcontrol.wait until
@@ -1113,7 +1112,19 @@ template <typename T, bool MULTI> static cudaError_t launch_nms_t(const NmsParam
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, nms_kernel<T, MULTI>, P);
+    return cudaLaunchKernelEx(&cfg, nms_kernel<T, MULTI, MINB>, P);
+}
+
+template <typename T, bool MULTI> static cudaError_t launch_nms_v(const NmsParams& P, cudaStream_t stream) {
+    // One CTA per (task, image) segment.  With at most one segment per SM the 128-register build runs (config 2:
+    // 63.5 -> 47.1 us, config 4: 79.9 -> 70.7 us); with more segments two CTAs must share an SM and the 64-register
+    // build is the faster one (config 3, 192 segments: 59.4 vs 69.6 us) -- profiles/r01_nms.md
+    int minb = 2, dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        P.T * P.B <= sms)
+        minb = 1;
+    if (const char* ev = getenv("CERB_DEBUG_NMS_MINB")) minb = atoi(ev) == 1 ? 1 : 2;  // tools/ and tests only
+    return minb == 1 ? launch_nms_t<T, MULTI, 1>(P, stream) : launch_nms_t<T, MULTI, 2>(P, stream);
 }
 
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream) {
@@ -1121,6 +1132,6 @@ cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream) 
     // multi_label &= nc > 1 (general.py:419): with nc == 1 both modes select the same candidates
     const bool multi = P.multi_label != 0;
     if (dtype == CERB_DTYPE_F16)
-        return multi ? launch_nms_t<__half, true>(P, stream) : launch_nms_t<__half, false>(P, stream);
-    return multi ? launch_nms_t<float, true>(P, stream) : launch_nms_t<float, false>(P, stream);
+        return multi ? launch_nms_v<__half, true>(P, stream) : launch_nms_v<__half, false>(P, stream);
+    return multi ? launch_nms_v<float, true>(P, stream) : launch_nms_v<float, false>(P, stream);
 }

@@ -137,12 +137,16 @@ def _assert_rows_equal(got, want, ctx=""):
         assert torch.equal(a, b), f"{ctx} image {i}: rows differ"
 
 
+@pytest.mark.parametrize("minb", [1, 2])
 @pytest.mark.parametrize("chunking", [(0, 0), (16, 1), (64, 7), (300, 300)])
 @pytest.mark.parametrize("name", golden_names("nms"))
-def test_nms_golden_bit_exact(ops, name, chunking):
+def test_nms_golden_bit_exact(ops, name, chunking, minb, monkeypatch):
+    """Every golden vector through both register builds of the NMS kernel (minb 1: 128 registers, used when each segment
+    gets its own SM; minb 2: 64 registers, two CTAs per SM) and four chunking settings."""
     from cerberusdet_b200 import _lib
     from cerberusdet_b200.nms import non_max_suppression
 
+    monkeypatch.setenv("CERB_DEBUG_NMS_MINB", str(minb))
     g = load_golden(name)
     if chunking != (0, 0) and g["pred"].shape[2] > 4000 and chunking[0] < 300:
         pytest.skip("tiny chunks on the large vectors only repeat the same paths slowly")
@@ -170,11 +174,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("minb", [1, 2])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_nms_vs_oracle(ops, case):
+def test_nms_vs_oracle(ops, case, minb, monkeypatch):
     from cerberusdet_b200.nms import non_max_suppression
     from oracle import ref_port as rp
 
+    monkeypatch.setenv("CERB_DEBUG_NMS_MINB", str(minb))
     bsz, nc, anchors, dtype, regime, kw = CASES[case]
     pred = synth_prediction(bsz, nc, anchors, seed=100 + case, dtype=dtype, regime=regime)
     want = rp.nms_port(pred, greedy="c", **kw)
