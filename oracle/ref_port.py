@@ -32,7 +32,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -245,3 +245,21 @@ def bbox_decode_port(anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> to
     dist = pred_dist.view(b, a, 4, c // 4).softmax(3).matmul(proj.type(pred_dist.dtype))
     lt, rb = torch.split(dist, 2, -1)
     return torch.cat((anchor_points - lt, anchor_points + rb), -1)
+
+
+# --------------------------------------------------------------------------- head tail (the checker is ready, the kernel is round 2)
+def head_tail_port(box_feats: Sequence[torch.Tensor], cls_feats: Sequence[torch.Tensor], box_w: Sequence[torch.Tensor],
+                   box_b: Sequence[torch.Tensor], cls_w: Sequence[torch.Tensor], cls_b: Sequence[torch.Tensor],
+                   strides: Sequence[float]) -> Tuple[torch.Tensor, list]:
+    """The step right before the path plus the path: the LAST 1x1 convolutions of the two towers of every level
+    (``cv2[i][-1]``: c2 -> 64 and ``cv3[i][-1]``: c3 -> nc, models/yolo.py:81-84), the channel concat (yolo.py:89-90) and
+    the eval decode (yolo.py:93-99).
+
+    ``box_feats[l]`` ``[B, c2, H_l, W_l]`` / ``cls_feats[l]`` ``[B, c3, H_l, W_l]`` are the inputs of those last
+    convolutions; ``box_w[l]`` ``[64, c2, 1, 1]``, ``cls_w[l]`` ``[nc, c3, 1, 1]`` and the biases are their parameters.
+    Returns ``(y [B, 4+nc, A], raw levels [B, 64+nc, H_l, W_l])`` like ``Detect.forward`` in eval mode."""
+    raw = []
+    for l in range(len(box_feats)):
+        raw.append(torch.cat((F.conv2d(box_feats[l], box_w[l], box_b[l]), F.conv2d(cls_feats[l], cls_w[l], cls_b[l])), 1))
+    nc = int(cls_w[0].shape[0])
+    return decode_port(raw, nc, strides), raw

@@ -98,3 +98,21 @@ def test_bbox_decode_port_bit_exact(name):
     assert torch.equal(out.detach(), torch.from_numpy(g["out"]))
     (grad_in,) = torch.autograd.grad(out, pred, torch.from_numpy(g["grad_out"]))
     assert torch.equal(grad_in, torch.from_numpy(g["grad_in"]))
+
+
+# ------------------------------------------------------------------ head tail: the checker, ahead of the kernel
+@pytest.mark.parametrize("name", golden_names("headtail"))
+def test_head_tail_port_bit_exact(name):
+    """Last 1x1 convs of both towers + concat + decode, restated in the oracle, against what the unmodified reference
+    Detect module (real conv towers, eval mode) returned for the captured inputs of those convs
+    (oracle/gen_golden_headtail.py)."""
+    from oracle import ref_port as rp
+
+    g = load_golden(name)
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    y, raw = rp.head_tail_port([t(f"box_feat{i}") for i in range(3)], [t(f"cls_feat{i}") for i in range(3)],
+                               [t(f"box_w{i}") for i in range(3)], [t(f"box_b{i}") for i in range(3)],
+                               [t(f"cls_w{i}") for i in range(3)], [t(f"cls_b{i}") for i in range(3)], (8.0, 16.0, 32.0))
+    for i in range(3):
+        assert torch.equal(raw[i], t(f"raw{i}")), f"raw level {i}"
+    assert torch.equal(y, t("y"))
