@@ -522,3 +522,40 @@ def test_bbox_decode_rejects_bad_arguments(ops):
         ops.bbox_decode(ap.cuda(), torch.zeros(1, 11, 64, device="cuda"))  # anchor count mismatch
     out = ops.bbox_decode(torch.zeros(0, 2, device="cuda"), torch.zeros(2, 0, 64, device="cuda"))
     assert tuple(out.shape) == (2, 0, 4)
+
+
+# ------------------------------------------------------------------ the bench's launch mode: one CUDA graph (decode -> NMS, PDL edge)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_cuda_graph_replay_equals_eager(ops, dtype):
+    """bench.py replays decode -> NMS as ONE captured CUDA graph; the NMS kernel is launched with programmatic stream
+    serialization, so inside the graph it hangs off the decode kernel by a programmatic dependency.  Replays on fresh
+    inputs (copied into the captured buffers) must give exactly the eager results, replay after replay."""
+    ncs, imgsz, bsz = [20, 19, 12], (640, 640), 4
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
+    batches = [synth_heads(range(k * bsz, (k + 1) * bsz), ncs, imgsz, dtype, "iid", cfg=3) for k in range(3)]
+    static = [[_dev(x).clone() for x in lv] for lv in batches[0]]
+    eager = []
+    for heads in batches:
+        ys = ops.decode_heads([[_dev(x) for x in lv] for lv in heads], STRIDES)
+        d, c = ops.nms_batched(ys, **kw)
+        eager.append((d.clone(), c.clone()))
+    for _ in range(2):  # warm-up on the side stream, as torch asks for before a capture
+        ops.nms_batched(ops.decode_heads(static, STRIDES), **kw)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            ys = ops.decode_heads(static, STRIDES)
+            d_static, c_static = ops.nms_batched(ys, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    for rep in range(2):
+        for k, heads in enumerate(batches):
+            for lv_s, lv in zip(static, heads):
+                for xs, x in zip(lv_s, lv):
+                    xs.copy_(_dev(x))
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(c_static, eager[k][1]), f"counts differ: replay {rep} batch {k}"
+            assert torch.equal(d_static, eager[k][0]), f"rows differ: replay {rep} batch {k}"
