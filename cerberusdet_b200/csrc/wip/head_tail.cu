@@ -283,3 +283,58 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
 // 2*(kb2+kb3)*64*128 + kb2*64*128 + kb3*w3_rows*128 + 64 bytes, cudaFuncAttributeMaxDynamicSharedMemorySize,
 // grid = B * ceil(hw / 128), one launch per (task, level).  TMEM: 512 columns per CTA -> exactly one CTA per SM may hold
 // an allocation; shrink HT_TMEM_COLS to 128 when ncp <= 64 so that several CTAs can share an SM.
+
+// ------------------------------------------------------------------ host side of the draft (one launch per (task, level))
+#include <stdio.h>
+
+typedef CUresult (*HtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ht_encode(HtEncodeTiledFn enc, CUtensorMap* map, const void* base, int rows, int hw) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)hw, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)hw * 2};
+    const cuuint32_t box[2] = {64, HT_KBLOCK};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+               ? 0
+               : -1;
+}
+
+// fp16 only.  u2 [B, c2, H, W], u3 [B, c3, H, W], w2 [64, c2], b2 [64], w3 [nc, c3], b3 [nc]; y [B, 4+nc, A] (this level's
+// anchors start at aoff), smax optional.  Returns 0, or a negative code with a message on stderr (draft: no error plumbing).
+extern "C" int cerb_wip_head_tail(const void* u2, const void* u3, const void* w2, const void* b2, const void* w3, const void* b3,
+                                  int B, int c2, int c3, int nc, int H, int W, float stride, int A, int aoff, void* y,
+                                  void* smax, void* stream) {
+    const int hw = H * W;
+    if (c2 % 16 || c3 % 16 || hw % 8 || nc < 1 || nc > 256) {
+        fprintf(stderr, "cerb_wip_head_tail: need c2 %% 16 == 0, c3 %% 16 == 0, H*W %% 8 == 0, 1 <= nc <= 256\n");
+        return -1;
+    }
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return -2;
+    HtEncodeTiledFn enc = reinterpret_cast<HtEncodeTiledFn>(p);
+    HeadTailParams P;
+    if (ht_encode(enc, &P.map_u2, u2, B * c2, hw) || ht_encode(enc, &P.map_u3, u3, B * c3, hw)) return -3;
+    P.w2 = (const __half*)w2; P.b2 = (const __half*)b2; P.w3 = (const __half*)w3; P.b3 = (const __half*)b3;
+    P.y = (__half*)y; P.smax = (__half*)smax;
+    P.B = B; P.hw = hw; P.W = W; P.A = A; P.aoff = aoff; P.nc = nc; P.c2 = c2; P.c3 = c3; P.stride = stride;
+    const int ncp = (nc + 15) & ~15, kb2 = (c2 + HT_KBLOCK - 1) / HT_KBLOCK, kb3 = (c3 + HT_KBLOCK - 1) / HT_KBLOCK;
+    const int w3_rows = (ncp + 7) & ~7;
+    const size_t smem = (size_t)2 * (kb2 + kb3) * HT_KBLOCK * 128 + (size_t)kb2 * 64 * 128 + (size_t)kb3 * w3_rows * 128 + 64;
+    int dev = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)smem_max) {
+        fprintf(stderr, "cerb_wip_head_tail: tile needs %zu B of shared memory (K ring not written yet)\n", smem);
+        return -4;
+    }
+    if (cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -5;
+    const int tiles = B * ((hw + HT_TILE - 1) / HT_TILE);
+    head_tail_kernel<<<tiles, HT_THREADS, smem, (cudaStream_t)stream>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}

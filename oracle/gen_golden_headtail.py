@@ -24,6 +24,7 @@ CASES = [
     # name, nc, ch, B, (H, W) of P3, dtype
     ("headtail_f32_nc20", 20, (32, 64, 64), 2, (16, 24), torch.float32),
     ("headtail_f16_nc12", 12, (64, 64, 128), 1, (16, 16), torch.float16),
+    ("headtail_f16_nc20_v8x", 20, (320, 640, 640), 1, (16, 16), torch.float16),  # yolov8x widths: c2 = 80, c3 = 320
 ]
 
 
