@@ -32,11 +32,8 @@ struct PipeParams {
     unsigned char row_trow[PIPE_MAX_ROWS];  // task * L + level
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-// src_bytes = 0 reads nothing (the slot is zero-filled): a branch-free "maybe prefetch" that the scheduler
-// cannot sink below the arithmetic the way it sinks a conditional block
+// cp_async16_pred: 16-byte cp.async with a source size.  src_bytes = 0 reads nothing (the slot is zero-filled): a
+// branch-free "maybe prefetch" that the scheduler cannot sink below the arithmetic the way it sinks a conditional block.
 #ifndef CERB_NO_L2_HINTS
 // raw heads are read exactly once: mark their lines evict-first so that y and the score summary (written here, read by
 // the NMS kernel right after) stay in the 126 MB L2 instead of being pushed out by 261 MB of streaming input
