@@ -27,6 +27,8 @@ EXPORTS = (
     "cerb_val_match",
     "cerb_bbox_decode_fwd",
     "cerb_bbox_decode_bwd",
+    "cerb_debug_set",
+    "cerb_debug_reset",
     "cerb_debug_set_chunking",
     "cerb_debug_set_hist_sample",
 )
@@ -76,12 +78,26 @@ def load() -> ctypes.CDLL:
     lib.cerb_bbox_decode_fwd.argtypes = [vp, vp, lg, i, i, i, vp, vp]
     lib.cerb_bbox_decode_bwd.restype = i
     lib.cerb_bbox_decode_bwd.argtypes = [vp, vp, lg, i, i, vp, vp]
+    if hasattr(lib, "cerb_debug_set") or "CERB_LIB" not in os.environ:  # (tools/ A/B runs may load an older build)
+        lib.cerb_debug_set.restype = i
+        lib.cerb_debug_set.argtypes = [ctypes.c_char_p, i]
+        lib.cerb_debug_reset.restype = i
+        lib.cerb_debug_reset.argtypes = []
     lib.cerb_debug_set_chunking.restype = i
     lib.cerb_debug_set_chunking.argtypes = [i, i]
     lib.cerb_debug_set_hist_sample.restype = i
     lib.cerb_debug_set_hist_sample.argtypes = [i]
     _lib = lib
     return lib
+
+
+def debug_set(name: str, value: int) -> None:
+    """Thread-local test / tools knob (include/cerb_post.h: cerb_debug_set)."""
+    check(load().cerb_debug_set(name.encode(), int(value)))
+
+
+def debug_reset() -> None:
+    load().cerb_debug_reset()
 
 
 def last_error() -> str:

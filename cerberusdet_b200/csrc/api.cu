@@ -9,7 +9,50 @@
 #include "cerb_kernels.h"
 
 static thread_local char g_err[512] = "";
-static int g_chunk_cap = 0, g_chunk_first = 0, g_hist_sample = 0;
+
+// ---- test / tools knobs.  Results never depend on any of them (the parity tests run the paths they select against
+// each other).  A knob set through cerb_debug_set() is THREAD-LOCAL: it affects only calls made by the thread that set
+// it, so the library stays re-entrant; the CERB_DEBUG_* environment variables (tools/ A/B runs, one process per
+// variant) are read ONCE per process.
+enum Knob {
+    K_DECODE_PIPE,    // 0 = register kernel (decode.cu), otherwise the pipelined kernel (value = variant id in CERB_DECODE_VARIANTS builds)
+    K_DECODE_ORDER,   // DecodeParams::interleave_parts
+    K_DECODE_VEC,     // cap on the anchors per thread
+    K_DECODE_L2HINT,  // force the L2 evict-first input policy on / off
+    K_NMS_MINB,       // 1 = 128-register NMS build, 2 = 64-register build
+    K_NMS_PDL,        // 0 = launch the NMS kernel without programmatic stream serialization
+    K_CHUNK_CAP,      // lazy top-k: chunk capacity (16..4096)
+    K_CHUNK_FIRST,    // lazy top-k: first chunk target
+    K_HIST_SAMPLE,    // stride of the estimating histogram
+    K_COUNT
+};
+static const char* const kKnobName[K_COUNT] = {"decode_pipe", "decode_order", "decode_vec", "decode_l2hint", "nms_minb",
+                                               "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample"};
+static const char* const kKnobEnv[K_COUNT] = {"CERB_DEBUG_DECODE_PIPE", "CERB_DEBUG_DECODE_ORDER", "CERB_DEBUG_DECODE_VEC",
+                                              "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL",
+                                              nullptr, nullptr, nullptr};
+struct KnobTable {
+    int v[K_COUNT];
+    bool set[K_COUNT];
+};
+static const KnobTable& env_knobs() {
+    static const KnobTable t = [] {
+        KnobTable k;
+        memset(&k, 0, sizeof(k));
+        for (int i = 0; i < K_COUNT; ++i)
+            if (kKnobEnv[i])
+                if (const char* ev = getenv(kKnobEnv[i])) { k.v[i] = atoi(ev); k.set[i] = true; }
+        return k;
+    }();
+    return t;
+}
+static thread_local KnobTable g_knobs = {};
+static bool knob(Knob k, int* out) {
+    if (g_knobs.set[k]) { *out = g_knobs.v[k]; return true; }
+    const KnobTable& e = env_knobs();
+    if (e.set[k]) { *out = e.v[k]; return true; }
+    return false;
+}
 
 void cerb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -26,32 +69,40 @@ void cerb_set_error(const char* fmt, ...) {
         }                             \
     } while (0)
 
-// default decode kernel per dtype (profiles/r01_decode.md, "software-pipelined variant"): items per thread of the pipelined kernel, 0 = decode.cu's
-#ifndef CERB_DECODE_PIPE_F16
-#define CERB_DECODE_PIPE_F16 2
-#endif
-#ifndef CERB_DECODE_PIPE_F32
-#define CERB_DECODE_PIPE_F32 1
-#endif
-#define CERB_DECODE_PIPE_DEFAULT(dtype) ((dtype) == CERB_F16 ? CERB_DECODE_PIPE_F16 : CERB_DECODE_PIPE_F32)
-
 static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 extern "C" int cerb_version(void) { return 100; }
 extern "C" const char* cerb_last_error(void) { return g_err; }
 
+extern "C" int cerb_debug_set(const char* name, int value) {
+    REQUIRE(name != nullptr, "cerb_debug_set: null knob name");
+    for (int i = 0; i < K_COUNT; ++i)
+        if (strcmp(name, kKnobName[i]) == 0) {
+            g_knobs.v[i] = value;
+            g_knobs.set[i] = true;
+            return 0;
+        }
+    cerb_set_error("cerb_debug_set: unknown knob '%s'", name);
+    return CERB_EINVAL;
+}
+extern "C" int cerb_debug_reset(void) {
+    memset(&g_knobs, 0, sizeof(g_knobs));
+    return 0;
+}
+
 extern "C" int cerb_debug_set_chunking(int chunk_cap, int chunk_first) {
-    if (chunk_cap == 0 && chunk_first == 0) { g_chunk_cap = g_chunk_first = 0; return 0; }
+    if (chunk_cap == 0 && chunk_first == 0) { g_knobs.set[K_CHUNK_CAP] = g_knobs.set[K_CHUNK_FIRST] = false; return 0; }
     REQUIRE(chunk_cap >= 16 && chunk_cap <= 4096, "chunk_cap must be in [16, 4096], got %d", chunk_cap);
     REQUIRE(chunk_first >= 1, "chunk_first must be >= 1, got %d", chunk_first);
-    g_chunk_cap = chunk_cap;
-    g_chunk_first = chunk_first;
+    g_knobs.v[K_CHUNK_CAP] = chunk_cap; g_knobs.set[K_CHUNK_CAP] = true;
+    g_knobs.v[K_CHUNK_FIRST] = chunk_first; g_knobs.set[K_CHUNK_FIRST] = true;
     return 0;
 }
 
 extern "C" int cerb_debug_set_hist_sample(int stride) {
     REQUIRE(stride >= 0 && stride <= 64, "hist sample stride must be in [0, 64], got %d", stride);
-    g_hist_sample = stride;
+    g_knobs.v[K_HIST_SAMPLE] = stride;
+    g_knobs.set[K_HIST_SAMPLE] = stride != 0;
     return 0;
 }
 
@@ -74,7 +125,7 @@ static int decode_common(const void* const* lvl, const void* const* cls_lvl, con
     memset(&P, 0, sizeof(P));
     P.T = T; P.L = L; P.B = B; P.nrows = T * L;
     P.interleave_parts = dtype == CERB_F32 ? 1 : 2;  // measured best per dtype (profiles/r01_decode.md)
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_ORDER")) P.interleave_parts = atoi(ev);  // tools/ only
+    (void)knob(K_DECODE_ORDER, &P.interleave_parts);
     const size_t elt = dtype == CERB_F16 ? 2 : 4;
     int vec = (int)(16 / elt);
     long A = 0;
@@ -108,7 +159,7 @@ static int decode_common(const void* const* lvl, const void* const* cls_lvl, con
             }
         }
     }
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_VEC")) { int v = atoi(ev); if (v >= 1 && v < vec) vec = v; }  // tools/ only
+    { int v = 0; if (knob(K_DECODE_VEC, &v) && v >= 1 && v < vec) vec = v; }
     if (B == 0) return 0;
     // the score summary (one maximum per 16-byte score vector) needs the full 128-bit path
     if (smax != nullptr && vec == (int)(16 / elt)) {
@@ -130,18 +181,15 @@ static int decode_common(const void* const* lvl, const void* const* cls_lvl, con
         int dev = 0, l2 = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess)
             P.l2_evict_first = out_bytes <= (size_t)l2 / 4 * 3;
-        if (const char* ev = getenv("CERB_DEBUG_DECODE_L2HINT")) P.l2_evict_first = atoi(ev);  // tools/ only
+        (void)knob(K_DECODE_L2HINT, &P.l2_evict_first);
     }
     cudaError_t e = cudaErrorInvalidConfiguration;
-    // The TMA-pipelined kernel (decode_tma.cu) is kept as a measured alternative; the register-resident kernel is
-    // faster on B200 for both dtypes (profiles/r01_decode.md), so it is the default.
-    bool use_tma = false;
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_TMA")) use_tma = cls_lvl == nullptr && vec == (int)(16 / elt) && atoi(ev) != 0;  // tools/ only
-    if (use_tma) e = cerb_launch_decode_tma(P, dtype, (cudaStream_t)stream);
-    // software-pipelined kernel (decode_pipe.cu): items per thread, 0 = the register-resident kernel
-    int pipe_ipt = CERB_DECODE_PIPE_DEFAULT(dtype);
-    if (const char* ev = getenv("CERB_DEBUG_DECODE_PIPE")) pipe_ipt = atoi(ev);  // tools/ and tests only
-    if (!use_tma && pipe_ipt > 0 && vec == (int)(16 / elt)) e = cerb_launch_decode_pipe(P, dtype, pipe_ipt, (cudaStream_t)stream);
+    // software-pipelined kernel (decode_pipe.cu) whenever every row allows 16-byte vectors, else (or with the
+    // decode_pipe knob at 0) the register-resident kernel of decode.cu.  (The persistent TMA variant measured in round 1
+    // is slower on B200 and no longer part of the library: csrc/experiments/decode_tma.cu, profiles/r01_decode.md.)
+    int pipe = 1;
+    (void)knob(K_DECODE_PIPE, &pipe);
+    if (pipe != 0 && vec == (int)(16 / elt)) e = cerb_launch_decode_pipe(P, dtype, pipe, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) {
         (void)cudaGetLastError();
         e = cerb_launch_decode(P, dtype, vec, (cudaStream_t)stream);
@@ -249,12 +297,19 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
         REQUIRE(aligned_to(workspace, 16), "cerb_nms: workspace must be 16-byte aligned");
         P.kept_ws = (float*)workspace;
     }
-    P.chunk_cap = g_chunk_cap ? g_chunk_cap : 4096;
-    int first = g_chunk_first ? g_chunk_first : (max_det + max_det / 8 + 32);
-    if (first < 128 && !g_chunk_first) first = 128;
+    P.chunk_cap = 4096;
+    (void)knob(K_CHUNK_CAP, &P.chunk_cap);
+    int first = max_det + max_det / 8 + 32;
+    if (first < 128) first = 128;
+    (void)knob(K_CHUNK_FIRST, &first);
     if (first > P.chunk_cap) first = P.chunk_cap;
     P.chunk_first = first;
-    P.hist_sample = g_hist_sample ? g_hist_sample : 8;
+    P.hist_sample = 8;
+    (void)knob(K_HIST_SAMPLE, &P.hist_sample);
+    P.force_minb = 0;
+    (void)knob(K_NMS_MINB, &P.force_minb);
+    P.pdl = 1;
+    (void)knob(K_NMS_PDL, &P.pdl);
     // Class shortcut (see nms.cu): exact when the offsets and the window ends are integers small enough
     // for every fp32 sum  coordinate-bound + class * gap  to be exact (true for the reference's 7680).
     P.class_shortcut = 0;

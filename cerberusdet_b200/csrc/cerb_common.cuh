@@ -89,13 +89,54 @@ __host__ __device__ constexpr uint32_t half2_bits_of_ints(int lo, int hi) {
 static_assert(half_bits_of_int(1) == 0x3C00 && half_bits_of_int(3) == 0x4200 && half_bits_of_int(9) == 0x4880 &&
               half_bits_of_int(15) == 0x4B80, "half encoding of the DFL bin weights");
 
+// ---- packed fp32 pairs (sm_100a: PTX fma.rn.f32x2 / add.rn.f32x2 / mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2): two
+// IEEE fp32 operations (each rounded exactly like the scalar instruction) for one issue slot.  The decode kernels are
+// issue-bound for half inputs (profiles/r01_decode.md), so every elementwise fp32 step is done on pairs.
+#ifndef CERB_F32X2
+#define CERB_F32X2 1
+#endif
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if CERB_F32X2
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+#if CERB_F32X2
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+#endif
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+#if CERB_F32X2
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#endif
+}
+
 // Expected DFL distance of one box side: sum_k k * softmax(x)_k over the 16 bins (reference DFL.forward,
 // models/yolo.py:57-59).  Rounding points follow the reference for half tensors: probabilities are rounded
 // to half (softmax output), the frozen 1x1 conv accumulates in fp32 and rounds once.  Max, sum and the
-// weighted sum are evaluated as short trees / 4 partial sums so the 16 bins give instruction-level
-// parallelism instead of three 16-long dependency chains.
+// weighted sum are short trees / 4 partial sums (instruction-level parallelism instead of three 16-long
+// dependency chains); the scale-and-shift before the exponentials, the sum and the normalisation run on
+// packed fp32 pairs (bins k, k+1).  dfl_expectation_acc returns the fp32 accumulator BEFORE its final rounding.
 #define CERB_LOG2E 1.4426950408889634f
-template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x)[CERB_REG_MAX]) {
+template <typename T> __device__ __forceinline__ float dfl_expectation_acc(float (&x)[CERB_REG_MAX]) {
 #ifdef CERB_EXPERIMENT_COPY_ONLY  // tools/ only: memory floor of this access pattern
     float t = 0.f;
 #pragma unroll
@@ -106,14 +147,18 @@ template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x
     float m1 = fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]));
     float m2 = fmaxf(fmaxf(x[8], x[9]), fmaxf(x[10], x[11]));
     float m3 = fmaxf(fmaxf(x[12], x[13]), fmaxf(x[14], x[15]));
-    const float mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * CERB_LOG2E;
+    const float nmb = -(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * CERB_LOG2E);
+    float2 e[CERB_REG_MAX / 2];
 #pragma unroll
-    for (int k = 0; k < CERB_REG_MAX; ++k) x[k] = fast_ex2(fmaf(x[k], CERB_LOG2E, -mb));
-    const float s0 = (x[0] + x[1]) + (x[2] + x[3]);
-    const float s1 = (x[4] + x[5]) + (x[6] + x[7]);
-    const float s2 = (x[8] + x[9]) + (x[10] + x[11]);
-    const float s3 = (x[12] + x[13]) + (x[14] + x[15]);
-    const float inv = fast_rcp((s0 + s1) + (s2 + s3));
+    for (int k = 0; k < CERB_REG_MAX / 2; ++k) {
+        const float2 u = ffma2(make_float2(x[2 * k], x[2 * k + 1]), make_float2(CERB_LOG2E, CERB_LOG2E), make_float2(nmb, nmb));
+        e[k] = make_float2(fast_ex2(u.x), fast_ex2(u.y));
+    }
+    const float2 s01 = fadd2(fadd2(e[0], e[1]), fadd2(e[2], e[3]));
+    const float2 s23 = fadd2(fadd2(e[4], e[5]), fadd2(e[6], e[7]));
+    const float2 s = fadd2(s01, s23);
+    const float inv = fast_rcp(s.x + s.y);
+    const float2 inv2 = make_float2(inv, inv);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #ifndef CERB_NO_FHFMA
     if constexpr (sizeof(T) == 2) {
@@ -121,28 +166,41 @@ template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x
         // rounding) -- the same value as fmaf((float)k, (float)p, acc) without the two unpacking converts per pair
 #pragma unroll
         for (int k = 0; k < CERB_REG_MAX; k += 4) {
-            const uint32_t p01 = pack_half2_rn(x[k] * inv, x[k + 1] * inv);
-            const uint32_t p23 = pack_half2_rn(x[k + 2] * inv, x[k + 3] * inv);
+            const float2 q01 = fmul2(e[k / 2], inv2), q23 = fmul2(e[k / 2 + 1], inv2);
+            const uint32_t p01 = pack_half2_rn(q01.x, q01.y);
+            const uint32_t p23 = pack_half2_rn(q23.x, q23.y);
             if (k != 0) a0 = fhfma_lo(p01, half2_bits_of_ints(k, k + 1), a0);  // 0 * p0 + 0 == +0
             a1 = fhfma_hi(p01, half2_bits_of_ints(k, k + 1), a1);
             a2 = fhfma_lo(p23, half2_bits_of_ints(k + 2, k + 3), a2);
             a3 = fhfma_hi(p23, half2_bits_of_ints(k + 2, k + 3), a3);
         }
+        return (a0 + a1) + (a2 + a3);
     } else
 #endif
     {
+        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < CERB_REG_MAX; k += 4) {
-            float p0, p1, p2, p3;
-            rnd2<T>(x[k] * inv, x[k + 1] * inv, p0, p1);
-            rnd2<T>(x[k + 2] * inv, x[k + 3] * inv, p2, p3);
-            a0 = fmaf((float)k, p0, a0);
-            a1 = fmaf((float)(k + 1), p1, a1);
-            a2 = fmaf((float)(k + 2), p2, a2);
-            a3 = fmaf((float)(k + 3), p3, a3);
+            float2 q01 = fmul2(e[k / 2], inv2), q23 = fmul2(e[k / 2 + 1], inv2);
+            rnd2<T>(q01.x, q01.y, q01.x, q01.y);
+            rnd2<T>(q23.x, q23.y, q23.x, q23.y);
+            a01 = ffma2(make_float2((float)k, (float)(k + 1)), q01, a01);
+            a23 = ffma2(make_float2((float)(k + 2), (float)(k + 3)), q23, a23);
         }
+        const float2 a = fadd2(a01, a23);
+        return a.x + a.y;
     }
-    return rnd<T>((a0 + a1) + (a2 + a3));
+}
+template <typename T> __device__ __forceinline__ float dfl_expectation(float (&x)[CERB_REG_MAX]) {
+    return rnd<T>(dfl_expectation_acc<T>(x));
+}
+
+// sigmoid of two logits at once (reference models/yolo.py:99): 1 / (1 + 2^(-x log2 e)), the scale and the "+ 1" on
+// packed fp32 pairs; the caller rounds to the tensor dtype
+__device__ __forceinline__ float2 sigmoid2(float2 x) {
+    const float2 t = fmul2(x, make_float2(-CERB_LOG2E, -CERB_LOG2E));
+    const float2 u = fadd2(make_float2(fast_ex2(t.x), fast_ex2(t.y)), make_float2(1.f, 1.f));
+    return make_float2(fast_rcp(u.x), fast_rcp(u.y));
 }
 
 // streaming 128-bit / 64-bit / scalar accesses (read once, write once: keep them out of L1)

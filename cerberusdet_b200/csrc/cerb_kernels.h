@@ -25,8 +25,6 @@ struct DecodeParams {
     int interleave_parts;        // block order: 0 parts contiguous per (task, level), 1 interleaved, 2 all DFL blocks first, then all class blocks
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);
-// persistent TMA-pipelined variant; needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one
-cudaError_t cerb_launch_decode_tma(const DecodeParams& P, int dtype, cudaStream_t stream);
 // software-pipelined variant (cp.async prefetch into per-thread shared-memory slots, ipt items per thread);
 // needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use the other one
 cudaError_t cerb_launch_decode_pipe(const DecodeParams& P, int dtype, int ipt, cudaStream_t stream);
@@ -54,6 +52,8 @@ struct NmsParams {
     int class_shortcut; // 1 if different-class tame boxes provably never intersect after the offset
     const void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V] from the decode kernel (else null)
     float tame_lo, tame_hi; // the window of "tame" un-offset coordinates, tame_hi - tame_lo == class_gap
+    int force_minb;         // host only: 0 = pick the register build per launch, 1 / 2 = force it (tests, tools)
+    int pdl;                // host only: launch with programmatic stream serialization (default 1)
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);

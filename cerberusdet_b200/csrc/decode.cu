@@ -69,45 +69,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
 
     if (part < 2) {
         // sides (l, r) -> cx, w   or   (t, b) -> cy, h      (utils/tal.py:198-204)
-        float dlo[VEC], dhi[VEC];
-#ifdef CERB_L2_PREFETCH  // measured slower on B200 (profiles/r01_decode.md); kept for the record
-        // while the first side is being reduced nothing of this warp is in flight: pull the second side's
-        // rows into L2 meanwhile (one 128-byte line per 128 / (16) lanes)
-        if (sizeof(T) * VEC == 16 && (threadIdx.x & 7) == 0) {
-            const T* nxt = in + (size_t)((part + 2) * CERB_REG_MAX) * hw;
-#pragma unroll
-            for (int k = 0; k < CERB_REG_MAX; ++k)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)k * hw));
-        }
-#endif
-#ifdef DEC_DOUBLE_BUFFER  // both sides' loads in flight before the first reduction (more registers, fewer warps)
-        {
-            Pack<T, VEC> va[CERB_REG_MAX], vb[CERB_REG_MAX];
-            dfl_load<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, va);
-            dfl_load<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, vb);
-            dfl_reduce<T, VEC>(va, dlo);
-            dfl_reduce<T, VEC>(vb, dhi);
-        }
-#else
+        DVec<T, VEC> dlo, dhi;
         dfl_side<T, VEC>(in + (size_t)(part * CERB_REG_MAX) * hw, hw, dlo);
         dfl_side<T, VEC>(in + (size_t)((part + 2) * CERB_REG_MAX) * hw, hw, dhi);
-#endif
-        const int W = P.w[level];
-        const float st = P.stride[level];
         Pack<T, VEC> oc, os;
-        int gx = a0 % W, gy = a0 / W;  // one division per thread; the VEC anchors then walk the grid row by row
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int g = (part == 0) ? gx : gy;
-            if (++gx >= W) { gx = 0; ++gy; }
-            const float ac = rnd<T>(rnd<T>((float)g) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
-            const float p1 = rnd<T>(ac - dlo[i]);
-            const float p2 = rnd<T>(ac + dhi[i]);
-            const float c = rnd<T>(rnd<T>(p1 + p2) * 0.5f);
-            const float sz = rnd<T>(p2 - p1);
-            oc.e[i] = from_f32<T>(c * st);
-            os.e[i] = from_f32<T>(sz * st);
-        }
+        axis_boxes<T, VEC>(dlo, dhi, a0, P.w[level], part == 0, P.stride[level], oc, os);
         store_pack<T, VEC>(out + (size_t)part * P.A, oc);
         store_pack<T, VEC>(out + (size_t)(part + 2) * P.A, os);
     } else {
@@ -129,22 +95,14 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_MINB) decode_kernel(const __g
             for (int u = 0; u < 4; ++u) vv[u] = load_pack<T, VEC>(cin + (size_t)(c + u) * hw);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float x = to_f32<T>(vv[u].e[i]);
-                    vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
-                }
+                sigmoid_pack<T, VEC>(vv[u]);
                 store_pack<T, VEC>(cout + (size_t)(c + u) * P.A, vv[u]);
                 if (smax != nullptr) smax[(size_t)(c + u) * srow] = pack_max<T, VEC>(vv[u]);
             }
         }
         for (; c < c1; ++c) {
             Pack<T, VEC> v1 = load_pack<T, VEC>(cin + (size_t)c * hw);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float x = to_f32<T>(v1.e[i]);
-                v1.e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
-            }
+            sigmoid_pack<T, VEC>(v1);
             store_pack<T, VEC>(cout + (size_t)c * P.A, v1);
             if (smax != nullptr) smax[(size_t)c * srow] = pack_max<T, VEC>(v1);
         }

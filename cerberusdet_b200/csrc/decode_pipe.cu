@@ -15,7 +15,8 @@
 // of one image (one 128-bit access per channel); a CTA owns DEC_THREADS * IPT consecutive items of a row and
 // a thread the items first + i * DEC_THREADS, so a warp still reads 512 contiguous bytes per channel.
 //   DFL thread:   groups = the 2 * IPT sides of its items; group g+1 streams in while group g is reduced.
-//   class thread: groups of 4 channels in a 4-deep ring (16 vectors in flight), across its IPT items.
+//   class thread: groups of 4 channels in a 4-deep ring (16 vectors in flight), across its CIPT items (class CTAs come
+//                 last in the grid, so fewer items per thread = shorter CTAs = a shorter tail).
 #include "decode_common.cuh"
 
 #ifndef PIPE_MINB
@@ -59,7 +60,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <typename T, int VEC, int IPT>
+template <typename T, int VEC, int IPT, int CIPT>
 __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(const __grid_constant__ PipeParams Q) {
     static_assert(sizeof(T) * VEC == 16, "the pipelined kernel moves 16-byte vectors");
     // the next kernel in the stream (NMS, launched with programmatic stream serialization) may be scheduled as this
@@ -93,9 +94,10 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
     const int hw = P.hw[level];
     const int nvec = hw / VEC;
     const int n_items = P.B * nvec;
-    const int first = ((int)blockIdx.x - Q.row_start[row]) * (DEC_THREADS * IPT) + (int)threadIdx.x;
+    const int ipt = kind < 2 ? IPT : CIPT;
+    const int first = ((int)blockIdx.x - Q.row_start[row]) * (DEC_THREADS * ipt) + (int)threadIdx.x;
     if (first >= n_items) return;
-    const int cnt = min(IPT, (n_items - first + DEC_THREADS - 1) / DEC_THREADS);  // my items: first + i * DEC_THREADS
+    const int cnt = min(ipt, (n_items - first + DEC_THREADS - 1) / DEC_THREADS);  // my items: first + i * DEC_THREADS
 
     const int nc = P.nc[task];
     // concatenated heads: box and class channels share one tensor; split heads: two tensors (models/yolo.py:90 unmaterialised)
@@ -121,9 +123,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
         };
         issue(side_ptr(0), 16);
         const int G = 2 * cnt;
-        const int W = P.w[level];
-        const float st = P.stride[level];
-        float dlo[VEC];
+        DVec<T, VEC> dlo;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
             const bool more = g + 1 < G;
@@ -133,11 +133,10 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
 #pragma unroll
             for (int k = 0; k < CERB_REG_MAX; ++k) v[k].raw = my[k * DEC_THREADS];
             issue(nxt, more ? 16 : 0);  // streams in while this side is reduced
-            float d[VEC];
+            DVec<T, VEC> d;
             dfl_reduce<T, VEC>(v, d);
             if ((g & 1) == 0) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) dlo[i] = d[i];
+                dlo = d;
             } else {
                 // dist2bbox(xywh) on one axis (utils/tal.py:198-204), * stride (yolo.py:98)
                 const int it = first + (g >> 1) * DEC_THREADS;
@@ -145,19 +144,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
                 const int a0 = vv * VEC;
                 T* __restrict__ out = ybase + (size_t)b * y_img + a0;
                 Pack<T, VEC> oc, os;
-                int gx = a0 % W, gy = a0 / W;
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const int gg = (kind == 0) ? gx : gy;
-                    if (++gx >= W) { gx = 0; ++gy; }
-                    const float ac = rnd<T>(rnd<T>((float)gg) + 0.5f);  // arange(dtype) + 0.5, tal.py:188-189
-                    const float p1 = rnd<T>(ac - dlo[i]);
-                    const float p2 = rnd<T>(ac + d[i]);
-                    const float c = rnd<T>(rnd<T>(p1 + p2) * 0.5f);
-                    const float sz = rnd<T>(p2 - p1);
-                    oc.e[i] = from_f32<T>(c * st);
-                    os.e[i] = from_f32<T>(sz * st);
-                }
+                axis_boxes<T, VEC>(dlo, d, a0, P.w[level], kind == 0, P.stride[level], oc, os);
                 store_pack<T, VEC>(out + (size_t)kind * P.A, oc);
                 store_pack<T, VEC>(out + (size_t)(kind + 2) * P.A, os);
             }
@@ -215,11 +202,7 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (cc + u < nc) {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float x = to_f32<T>(vv[u].e[i]);
-                        vv[u].e[i] = from_f32<T>(fast_rcp(1.f + fast_ex2(-x * LOG2E_F)));
-                    }
+                    sigmoid_pack<T, VEC>(vv[u]);
                     store_pack<T, VEC>(cout + (size_t)(cc + u) * P.A, vv[u]);
                     if (smax != nullptr) smax[(size_t)(cc + u) * srow] = pack_max<T, VEC>(vv[u]);
                 }
@@ -233,11 +216,10 @@ __global__ void __launch_bounds__(DEC_THREADS, PIPE_MINB) decode_pipe_kernel(con
     }
 }
 
-template <typename T, int VEC, int IPT> static cudaError_t launch_pipe_t(const DecodeParams& P, cudaStream_t stream) {
+template <typename T, int VEC, int IPT, int CIPT> static cudaError_t launch_pipe_t(const DecodeParams& P, cudaStream_t stream) {
     PipeParams q;
     q.d = P;
     int blocks = 0, r = 0;
-    const int per_block = DEC_THREADS * IPT;
     // block order (profiles/r01_decode.md): 2 = every DFL row of the launch first, then every class row (the
     // short streaming CTAs fill the tail); anything else = per (task, level): [l,r][t,b][classes]
     const bool box_first = P.interleave_parts == 2;
@@ -245,14 +227,14 @@ template <typename T, int VEC, int IPT> static cudaError_t launch_pipe_t(const D
         for (int t = 0; t < P.T; ++t)
             for (int l = 0; l < P.L; ++l) {
                 const long items = (long)P.B * (P.hw[l] / VEC);
-                const int nb = (int)((items + per_block - 1) / per_block);
                 const int k0 = box_first ? (pass == 0 ? 0 : 2) : 0;
                 const int k1 = box_first ? (pass == 0 ? 2 : 3) : 3;
                 for (int k = k0; k < k1; ++k) {
+                    const int per_block = DEC_THREADS * (k < 2 ? IPT : CIPT);
                     q.row_start[r] = blocks;
                     q.row_kind[r] = (unsigned char)k;
                     q.row_trow[r] = (unsigned char)(t * P.L + l);
-                    blocks += nb;
+                    blocks += (int)((items + per_block - 1) / per_block);
                     ++r;
                 }
             }
@@ -262,27 +244,43 @@ template <typename T, int VEC, int IPT> static cudaError_t launch_pipe_t(const D
     constexpr size_t smem = (size_t)PIPE_SLOT_VECS * DEC_THREADS * 16;
     // per launch, like launch_nms_t: function attributes are per device, and a process may drive several
     // (32 KB fits the default dynamic limit; the carve-out is what lets 5 CTAs = 165 KB share an SM)
-    cudaError_t e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaError_t e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT, CIPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    decode_pipe_kernel<T, VEC, IPT><<<blocks, DEC_THREADS, smem, stream>>>(q);
+    decode_pipe_kernel<T, VEC, IPT, CIPT><<<blocks, DEC_THREADS, smem, stream>>>(q);
     return cudaGetLastError();
 }
 
+// Items per thread (DFL rows, class rows) of the shipped instantiations: fp16 2 / PIPE_CIPT_F16, fp32 1 / 1
+// (profiles/r02_decode.md).  -DCERB_DECODE_VARIANTS also builds the other combinations for tools/ A/B runs
+// (ipt = 10 * IPT + CIPT selects one).
+#ifndef PIPE_IPT_F16
+#define PIPE_IPT_F16 2
+#endif
+#ifndef PIPE_CIPT_F16
+#define PIPE_CIPT_F16 1
+#endif
 // needs vec == 16 / sizeof(T); cudaErrorInvalidConfiguration = use decode.cu's kernel
 cudaError_t cerb_launch_decode_pipe(const DecodeParams& P, int dtype, int ipt, cudaStream_t stream) {
     if (dtype == CERB_DTYPE_F16) {
         switch (ipt) {
-            case 1: return launch_pipe_t<__half, 8, 1>(P, stream);
-            case 2: return launch_pipe_t<__half, 8, 2>(P, stream);
-            case 4: return launch_pipe_t<__half, 8, 4>(P, stream);
-            default: return cudaErrorInvalidConfiguration;
+#ifdef CERB_DECODE_VARIANTS
+            case 11: return launch_pipe_t<__half, 8, 1, 1>(P, stream);
+            case 21: return launch_pipe_t<__half, 8, 2, 1>(P, stream);
+            case 22: return launch_pipe_t<__half, 8, 2, 2>(P, stream);
+            case 42: return launch_pipe_t<__half, 8, 4, 2>(P, stream);
+            case 41: return launch_pipe_t<__half, 8, 4, 1>(P, stream);
+#endif
+            case 0: return cudaErrorInvalidConfiguration;
+            default: return launch_pipe_t<__half, 8, PIPE_IPT_F16, PIPE_CIPT_F16>(P, stream);
         }
     }
     switch (ipt) {
-        case 1: return launch_pipe_t<float, 4, 1>(P, stream);
-        case 2: return launch_pipe_t<float, 4, 2>(P, stream);
-        case 4: return launch_pipe_t<float, 4, 4>(P, stream);
-        default: return cudaErrorInvalidConfiguration;
+#ifdef CERB_DECODE_VARIANTS
+        case 21: return launch_pipe_t<float, 4, 2, 1>(P, stream);
+        case 22: return launch_pipe_t<float, 4, 2, 2>(P, stream);
+#endif
+        case 0: return cudaErrorInvalidConfiguration;
+        default: return launch_pipe_t<float, 4, 1, 1>(P, stream);
     }
 }

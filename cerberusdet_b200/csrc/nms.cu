@@ -1101,7 +1101,7 @@ template <typename T, bool MULTI, int MINB> static cudaError_t launch_nms_t(cons
     // launched with programmatic stream serialization: the CTAs may be scheduled as soon as every CTA of the previous
     // kernel has started (the decode kernels signal launch_dependents at entry) and block in griddepcontrol.wait until
     // it has completed -- hides the launch latency and the prologue behind the decode kernel's tail
-    static const bool pdl = getenv("CERB_DEBUG_NO_PDL") == nullptr;  // tools/ only
+    const bool pdl = P.pdl != 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(P.T * P.B));
     cfg.blockDim = dim3(NMS_THREADS);
@@ -1123,7 +1123,7 @@ template <typename T, bool MULTI> static cudaError_t launch_nms_v(const NmsParam
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
         P.T * P.B <= sms)
         minb = 1;
-    if (const char* ev = getenv("CERB_DEBUG_NMS_MINB")) minb = atoi(ev) == 1 ? 1 : 2;  // tools/ and tests only
+    if (P.force_minb) minb = P.force_minb == 1 ? 1 : 2;  // tests and tools
     return minb == 1 ? launch_nms_t<T, MULTI, 1>(P, stream) : launch_nms_t<T, MULTI, 2>(P, stream);
 }
 

@@ -15,6 +15,21 @@ import torch
 from .ops import decode_heads
 
 _RAW_FLAG = "_cerb_raw_heads"  # set by inference.raw_heads(): return the per-level tensors undecoded
+_STRIDES_ATTR = "_cerb_strides"  # (key, python floats): the head's strides without a device sync per forward
+
+
+def head_strides(head):
+    """``head.stride`` as Python floats.  ``attempt_load(..., map_location=device)`` leaves that tensor on the GPU, where
+    every ``float()`` is a blocking device->host copy behind the queued conv towers -- so the floats are read once and
+    kept on the module, keyed by the tensor object and its version (a replaced or rewritten stride is re-read)."""
+    st = head.stride
+    key = (id(st), getattr(st, "_version", 0)) if torch.is_tensor(st) else None
+    ent = getattr(head, _STRIDES_ATTR, None)
+    if ent is None or ent[0] != key or key is None:
+        vals = tuple(float(v) for v in (st.detach().cpu().tolist() if torch.is_tensor(st) else st))
+        ent = (key, vals)
+        object.__setattr__(head, _STRIDES_ATTR, ent)
+    return ent[1]
 
 
 def _level_cat(self, x):
@@ -56,6 +71,6 @@ def detect_forward(self, x):
 
         self.anchors, self.strides = make_anchor_tensors([t.shape[2:] for t in x], self.stride, x[0].dtype, x[0].device)
         self.shape = shape
-    strides = [float(s) for s in self.stride]
+    strides = head_strides(self)
     y = decode_heads([[t if t.is_contiguous() else t.contiguous() for t in x]], strides)[0]
     return y if self.export else (y, x)

@@ -15,8 +15,19 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import cross_task
-from .detect import _RAW_FLAG, SplitHeads
+from .detect import _RAW_FLAG, SplitHeads, head_strides
 from .ops import cross_task_merge, decode_heads, decode_heads_split, nms_batched
+
+
+def _reference_nms():
+    """The reference's own ``non_max_suppression`` (the saved original when ``patch.install()`` rebound the name)."""
+    try:
+        from cerberusdet.utils import general
+    except ImportError as exc:  # stand-alone use without the reference package: there is no CPU path of ours
+        raise TypeError("non-CUDA predictions need the reference package (cerberusdet) for its CPU non_max_suppression; "
+                        "cerberusdet_b200 has no CPU path") from exc
+    fn = general.non_max_suppression
+    return getattr(fn, "_cerb_reference", fn)
 
 
 @contextlib.contextmanager
@@ -79,10 +90,12 @@ class CerberusDetInference:
     _get_categories_map = staticmethod(cross_task.category_maps)
 
     def _head_strides(self, n_levels: int) -> List[float]:
-        for m in self.model.modules():
-            if hasattr(type(m), "_cerb_reference_forward") or type(m).__name__ == "Detect":
-                return [float(s) for s in m.stride]
-        return [float(s) for s in self.model.stride][:n_levels]
+        head = getattr(self, "_cerb_head", None)
+        if head is None:
+            head = next((m for m in self.model.modules()
+                         if hasattr(type(m), "_cerb_reference_forward") or type(m).__name__ == "Detect"), self.model)
+            self._cerb_head = head
+        return list(head_strides(head))[:n_levels]
 
     @torch.no_grad()
     def predict(
@@ -102,7 +115,9 @@ class CerberusDetInference:
         # 1. forward: every head hands over its raw per-level tensors
         with raw_heads(self.model):
             all_out = self.model(tensor)
-        tasks = list(all_out.keys())
+        # task order = the order of self.names (categories_inds_map), which is the order the reference's
+        # nms_between_tasks regroups the rows in (utils/general.py:497-505) -- the scan below is order-dependent
+        tasks = [t for t in self.categories_inds_map if t in all_out] + [t for t in all_out if t not in self.categories_inds_map]
         preds = [all_out[t][0] for t in tasks]
         if any(p is None for p in preds):  # raw mode was honoured: decode all heads in one launch
             levels = [all_out[t][1] for t in tasks]
@@ -111,14 +126,27 @@ class CerberusDetInference:
                 preds = decode_heads_split([lv.box for lv in levels], [lv.cls for lv in levels], strides)
             else:
                 preds = decode_heads(levels, self._head_strides(len(levels[0])))
-        # 2. one NMS launch over all (task, image) segments
-        dets, counts = nms_batched(preds, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det)
         bsz = tensor.shape[0]
+        on_path = all(p.is_cuda and p.dtype in (torch.float16, torch.float32) for p in preds)
+        if on_path:
+            # 2. one NMS launch over all (task, image) segments
+            dets, counts = nms_batched(preds, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det)
+        else:
+            # a CPU (or otherwise off-path) model: the reference's own per-task NMS, as patch.install() promises --
+            # the patch never changes what a non-CUDA run computes (cerberusdet_inference.py:125-135)
+            ref_nms = _reference_nms()
+            rows = [ref_nms(p, conf_thres, iou_thres, agnostic=agnostic_nms, max_det=max_det) for p in preds]
+            dets = torch.zeros((len(tasks), bsz, max_det, 6), dtype=torch.float32)
+            counts = torch.zeros((len(tasks), bsz), dtype=torch.int32)
+            for k, per_image in enumerate(rows):
+                for i, r in enumerate(per_image):
+                    dets[k, i, : r.shape[0]] = r.detach().float().cpu()
+                    counts[k, i] = r.shape[0]
         shapes = None
         if original_shape is not None:
             shapes = original_shape if isinstance(original_shape, list) else [original_shape] * bsz
         results = []
-        if len(tasks) * max_det <= 1024:
+        if on_path and len(tasks) * max_det <= cross_task.GPU_MAX_ROWS:
             # 3. cross-task merge + rescale on the GPU (one launch, one CTA per image), then ONE D2H copy
             offsets = [min(self.categories_inds_map[t].values()) if self.categories_inds_map[t] else 0 for t in tasks]
             scale = None

@@ -1,13 +1,14 @@
-"""torch custom ops ``cerb::decode`` and ``cerb::nms`` over the C ABI.
+"""torch custom ops over the C ABI of ``libcerb_post.so``: ``cerb::decode``, ``cerb::decode_split``, ``cerb::nms``,
+``cerb::nms_out`` (writes into caller buffers) and ``cerb::decode_nms``.  The Python wrappers below (``decode_heads``,
+``nms_batched``, ...) dispatch through these registered ops, so eager calls, CUDA-graph capture and ``torch.compile``
+all reach the same kernels.
 
-PyTorch is plumbing here (device memory, streams); the arithmetic is in
-``csrc/decode.cu`` and ``csrc/nms.cu``.  Inputs must be CUDA tensors: a CPU tensor
-raises ``TypeError`` -- there is no fallback.
+PyTorch is plumbing here (device memory, streams); the arithmetic is in ``csrc/decode_pipe.cu`` / ``csrc/decode.cu``
+and ``csrc/nms.cu``.  Inputs must be CUDA tensors: a CPU tensor raises ``TypeError`` -- there is no fallback.
 """
 from __future__ import annotations
 
 import ctypes
-import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -34,6 +35,21 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dense16(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (a contiguous view at an odd storage offset is copied)."""
+    x = x.contiguous()
+    return x if x.data_ptr() % 16 == 0 else x.clone(memory_format=torch.contiguous_format)
+
+
+def _summary_len(level_sizes: Sequence[int], elt: int) -> int:
+    """Row length of the score summary (``cerb_summary_row_len``), or 0 when a level rules the 128-bit path out."""
+    V = 16 // elt
+    if any(n % V for n in level_sizes):
+        return 0
+    n = sum(level_sizes) // V
+    return (n + V - 1) // V * V
 
 
 def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float],
@@ -66,7 +82,7 @@ def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Seq
             cbox = 64 if cls_levels is not None else 64 + nc[t]
             if tuple(x.shape) != (B, cbox, H[l], W[l]):
                 raise ValueError(f"task {t} level {l}: expected {(B, cbox, H[l], W[l])}, got {tuple(x.shape)}")
-            lv.append(x.contiguous())
+            lv.append(_dense16(x))
     cl = []
     if cls_levels is not None:
         for t in range(T):
@@ -76,9 +92,12 @@ def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Seq
                     raise TypeError("all head tensors must share device and dtype")
                 if tuple(c.shape) != (B, nc[t], H[l], W[l]):
                     raise ValueError(f"task {t} level {l}: expected class tensor {(B, nc[t], H[l], W[l])}, got {tuple(c.shape)}")
-                cl.append(c.contiguous())
+                cl.append(_dense16(c))
     ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
-    R = int(lib.cerb_summary_row_len(A, code))
+    # the score summary exists exactly when every level allows 16-byte vectors (inputs and outputs here are 16-byte
+    # aligned by construction), so its shape is a function of the shapes alone -- the fake kernel below relies on that
+    R = _summary_len([h * w for h, w in zip(H, W)], first.element_size())
+    assert R == 0 or R == int(lib.cerb_summary_row_len(A, code))
     sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
     written = ctypes.c_int(0)
     tail = (_lib.int_array(list(nc)), T, L, B, _lib.int_array(H), _lib.int_array(W),
@@ -90,27 +109,44 @@ def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Seq
         else:
             rc = lib.cerb_decode_split(_lib.ptr_array([x.data_ptr() for x in lv]), _lib.ptr_array([x.data_ptr() for x in cl]), *tail)
     _lib.check(rc)
-    if not written.value:
-        sm = [y.new_empty((0,)) for y in ys]
+    if bool(written.value) != (R > 0 and B > 0):
+        raise _lib.CerbLibraryError("cerb_decode: score summary state differs from what the shapes imply")
     return ys + sm
 
 
 @torch.library.custom_op("cerb::decode", mutates_args=())
 def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float]) -> List[torch.Tensor]:
-    """torch custom op over ``_decode_impl`` (for graphs / compile); the Python wrappers call the impl directly."""
+    """``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]`` from ``T*L`` raw head tensors (task-major); ``smax_t`` has a last
+    dimension of 0 when the shapes rule the score summary out."""
     return _decode_impl(levels, nc, strides)
+
+
+@torch.library.custom_op("cerb::decode_split", mutates_args=())
+def decode_split_op(box_levels: Sequence[torch.Tensor], cls_levels: Sequence[torch.Tensor], nc: Sequence[int],
+                    strides: Sequence[float]) -> List[torch.Tensor]:
+    """``cerb::decode`` on split heads (box channels and class channels in their own tensors)."""
+    return _decode_impl(box_levels, nc, strides, cls_levels=cls_levels)
+
+
+def _decode_fake(levels, nc, strides):
+    T = len(nc)
+    L = len(levels) // T
+    B = levels[0].shape[0]
+    sizes = [levels[l].shape[2] * levels[l].shape[3] for l in range(L)]
+    A = sum(sizes)
+    R = _summary_len(sizes, levels[0].element_size())
+    return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)] + [
+        levels[0].new_empty((B, nc[t], R)) for t in range(T)]
 
 
 @decode_op.register_fake
 def _(levels, nc, strides):
-    T = len(nc)
-    L = len(levels) // T
-    B = levels[0].shape[0]
-    A = sum(levels[l].shape[2] * levels[l].shape[3] for l in range(L))
-    V = 16 // levels[0].element_size()
-    R = (A // V + V - 1) // V * V
-    return [levels[0].new_empty((B, 4 + nc[t], A)) for t in range(T)] + [
-        levels[0].new_empty((B, nc[t], R)) for t in range(T)]
+    return _decode_fake(levels, nc, strides)
+
+
+@decode_split_op.register_fake
+def _(box_levels, cls_levels, nc, strides):
+    return _decode_fake(box_levels, nc, strides)
 
 
 def _nms_impl(
@@ -196,35 +232,83 @@ def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max
             preds[0].new_empty((T, B), dtype=torch.int32))
 
 
-# ----------------------------------------------------------------------------- score-summary registry
-class _Summary:
-    __slots__ = ("ref", "version", "smax")
+@torch.library.custom_op("cerb::nms_out", mutates_args=("dets", "counts"))
+def nms_out_op(
+    preds: Sequence[torch.Tensor],
+    conf_thres: float,
+    iou_thres: float,
+    classes: Optional[Sequence[int]],
+    agnostic: bool,
+    multi_label: bool,
+    max_det: int,
+    max_nms: int,
+    max_wh: float,
+    smax: Sequence[torch.Tensor],
+    dets: torch.Tensor,
+    counts: torch.Tensor,
+) -> None:
+    """``cerb::nms`` writing into caller-provided ``dets[T,B,max_det,6]`` / ``counts[T,B]`` (a gather buffer, a peer
+    GPU's mapped memory, a static CUDA-graph buffer)."""
+    _nms_impl(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax, (dets, counts))
 
 
-_SUMMARIES: "dict[int, _Summary]" = {}
+@nms_out_op.register_fake
+def _(preds, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, smax, dets, counts):
+    return None
+
+
+@torch.library.custom_op("cerb::decode_nms", mutates_args=())
+def decode_nms_op(
+    levels: Sequence[torch.Tensor],
+    nc: Sequence[int],
+    strides: Sequence[float],
+    conf_thres: float,
+    iou_thres: float,
+    classes: Optional[Sequence[int]],
+    agnostic: bool,
+    multi_label: bool,
+    max_det: int,
+    max_nms: int,
+    max_wh: float,
+) -> List[torch.Tensor]:
+    """Raw head tensors -> ``[dets[T,B,max_det,6], counts[T,B], y_0 .. y_{T-1}]`` in ONE library call
+    (``cerb_decode_nms``: both kernels back to back on the current stream, no host work in between)."""
+    return _decode_nms_impl(levels, nc, strides, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+
+
+@decode_nms_op.register_fake
+def _(levels, nc, strides, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+    T = len(nc)
+    B = levels[0].shape[0]
+    ys = _decode_fake(levels, nc, strides)[:T]
+    return [levels[0].new_empty((T, B, max_det, 6), dtype=torch.float32), levels[0].new_empty((T, B), dtype=torch.int32)] + ys
+
+
+# ----------------------------------------------------------------------------- score-summary hand-over
+_SUMMARY_ATTR = "_cerb_score_summary"
 
 
 def _remember_summary(y: torch.Tensor, smax: torch.Tensor) -> None:
-    """Remember that ``smax`` summarises ``y`` as it is right now.  ``find_summary`` hands it back only for
-    this very tensor (same storage, shape, and no in-place write since), so a stale summary is never used."""
-    if len(_SUMMARIES) > 64:
-        for k in [k for k, v in _SUMMARIES.items() if v.ref() is None]:
-            del _SUMMARIES[k]
-        if len(_SUMMARIES) > 64:
-            _SUMMARIES.clear()
-    ent = _Summary()
-    ent.ref, ent.version, ent.smax = weakref.ref(y), y._version, smax
-    _SUMMARIES[y.data_ptr()] = ent
+    """Attach ``smax`` (the decode kernel's score summary of ``y`` as it is right now) to the tensor OBJECT ``y``.
+    ``find_summary`` hands it back only for this very object while its version counter is unchanged, so a view, a copy
+    or a tensor written in place since never gets a stale summary; the summary dies with ``y``.
+
+    Not tracked (PyTorch keeps no version there): tensors created under ``torch.inference_mode()`` -- they simply get no
+    summary and NMS scans the scores itself -- and writes that bypass autograd's bookkeeping (``y.data[...] = ...``, a
+    foreign kernel writing through ``data_ptr()``): pass ``use_summary=False`` to ``nms_batched`` after such a write."""
+    if y.is_inference():
+        return
+    setattr(y, _SUMMARY_ATTR, (smax, y._version, y.data_ptr()))
 
 
 def find_summary(y: torch.Tensor):
-    ent = _SUMMARIES.get(y.data_ptr())
-    if ent is None:
+    ent = getattr(y, _SUMMARY_ATTR, None)
+    if ent is None or y.is_inference():
         return None
-    t = ent.ref()
-    if t is None or t is not y or y._version != ent.version or not y.is_contiguous():
+    smax, version, ptr = ent
+    if y._version != version or y.data_ptr() != ptr or not y.is_contiguous():
         return None
-    return ent.smax
+    return smax
 
 
 # ----------------------------------------------------------------------------- friendly wrappers
@@ -234,11 +318,11 @@ def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequenc
     The kernel also leaves a score summary per task, remembered for ``nms_batched``."""
     flat = [x for lv in task_levels for x in lv]
     nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
-    out = _decode_impl(flat, nc, [float(s) for s in strides])
+    out = decode_op(flat, nc, [float(s) for s in strides])
     T = len(nc)
     ys, sms = out[:T], out[T:]
     for y, sm in zip(ys, sms):
-        if sm.numel():
+        if sm.shape[-1]:
             _remember_summary(y, sm)
     return ys
 
@@ -249,12 +333,12 @@ def decode_heads_split(task_box_levels: Sequence[Sequence[torch.Tensor]], task_c
     ``task_cls_levels[t][l]`` = ``[B, nc_t, H_l, W_l]`` (cv3's) -- the reference's channel concat (models/yolo.py:89-90)
     is never materialised.  Same result, bit for bit, as ``decode_heads`` on the concatenated tensors."""
     nc = [int(lv[0].shape[1]) for lv in task_cls_levels]
-    out = _decode_impl([x for lv in task_box_levels for x in lv], nc, [float(s) for s in strides],
-                       cls_levels=[x for lv in task_cls_levels for x in lv])
+    out = decode_split_op([x for lv in task_box_levels for x in lv], [x for lv in task_cls_levels for x in lv], nc,
+                          [float(s) for s in strides])
     T = len(nc)
     ys, sms = out[:T], out[T:]
     for y, sm in zip(ys, sms):
-        if sm.numel():
+        if sm.shape[-1]:
             _remember_summary(y, sm)
     return ys
 
@@ -285,9 +369,12 @@ def nms_batched(
         found = [find_summary(p) for p in preds]
         if all(f is not None for f in found):
             smax = found
-    return _nms_impl(preds, float(conf_thres), float(iou_thres),
-                  None if classes is None else [int(c) for c in classes],
-                  bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax, out)
+    args = (preds, float(conf_thres), float(iou_thres), None if classes is None else [int(c) for c in classes],
+            bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)
+    if out is not None:
+        nms_out_op(*args, out[0], out[1])
+        return out
+    return nms_op(*args)
 
 
 def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Sequence[int], iou_thres: float,
@@ -316,27 +403,31 @@ def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Se
     return out, out_counts
 
 
-def decode_nms(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float], conf_thres: float = 0.25,
-               iou_thres: float = 0.45, classes: Optional[Sequence[int]] = None, agnostic: bool = False,
-               multi_label: bool = False, max_det: int = 300, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
-    """Raw head tensors -> padded detections in ONE library call (``cerb_decode_nms``: both kernels back to back on
-    the current stream).  Returns ``(dets[T,B,max_det,6], counts[T,B], ys)``."""
-    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
-    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+def _decode_nms_impl(levels, nc, strides, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
     lib = _lib.load()
-    T, L = len(task_levels), len(strides)
-    first = task_levels[0][0]
+    T = len(nc)
+    if T == 0 or len(levels) % T:
+        raise ValueError("levels must hold T*L tensors, task-major")
+    L = len(levels) // T
+    if len(strides) != L:
+        raise ValueError(f"expected {L} strides, got {len(strides)}")
+    first = levels[0]
     _require_cuda(first, "head tensors")
     code = _dtype_code(first)
     B = int(first.shape[0])
-    H = [int(x.shape[2]) for x in task_levels[0]]
-    W = [int(x.shape[3]) for x in task_levels[0]]
+    H = [int(levels[l].shape[2]) for l in range(L)]
+    W = [int(levels[l].shape[3]) for l in range(L)]
     A = sum(h * w for h, w in zip(H, W))
-    nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
-    lv = [x.contiguous() for row in task_levels for x in row]
+    lv = []
+    for t in range(T):
+        for l in range(L):
+            x = levels[t * L + l]
+            if x.device != first.device or x.dtype != first.dtype or tuple(x.shape) != (B, 64 + nc[t], H[l], W[l]):
+                raise ValueError(f"task {t} level {l}: expected {(B, 64 + nc[t], H[l], W[l])} {first.dtype} on {first.device}")
+            lv.append(_dense16(x))
     dev = first.device
     ys = [torch.empty((B, 4 + n, A), dtype=first.dtype, device=dev) for n in nc]
-    R = int(lib.cerb_summary_row_len(A, code))
+    R = _summary_len([h * w for h, w in zip(H, W)], first.element_size())
     sm = [torch.empty((B, n, max(R, 1)), dtype=first.dtype, device=dev) for n in nc]
     dets = torch.empty((T, B, max_det, 6), dtype=torch.float32, device=dev)
     counts = torch.empty((T, B), dtype=torch.int32, device=dev)
@@ -344,18 +435,32 @@ def decode_nms(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
         rc = lib.cerb_decode_nms(
-            _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(nc), T, L, B, _lib.int_array(H), _lib.int_array(W),
+            _lib.ptr_array([x.data_ptr() for x in lv]), _lib.int_array(list(nc)), T, L, B, _lib.int_array(H), _lib.int_array(W),
             _lib.float_array([float(s) for s in strides]), code, _lib.ptr_array([y.data_ptr() for y in ys]),
             _lib.ptr_array([x.data_ptr() for x in sm]) if R else None, float(conf_thres), float(iou_thres),
             _lib.int_array(list(classes)) if classes is not None else None, len(classes) if classes is not None else 0,
             int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh), dets.data_ptr(),
             counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(dev))
     _lib.check(rc)
-    return dets, counts, ys
+    return [dets, counts] + ys
+
+
+def decode_nms(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float], conf_thres: float = 0.25,
+               iou_thres: float = 0.45, classes: Optional[Sequence[int]] = None, agnostic: bool = False,
+               multi_label: bool = False, max_det: int = 300, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
+    """Raw head tensors -> padded detections in ONE library call (``cerb::decode_nms`` / ``cerb_decode_nms``: both kernels
+    back to back on the current stream).  Returns ``(dets[T,B,max_det,6], counts[T,B], ys)``."""
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
+    out = decode_nms_op([x for row in task_levels for x in row], nc, [float(s) for s in strides], float(conf_thres),
+                        float(iou_thres), None if classes is None else [int(c) for c in classes], bool(agnostic),
+                        bool(multi_label), int(max_det), int(max_nms), float(max_wh))
+    return out[0], out[1], out[2:]
 
 
 def match_batch(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, label_offsets: Sequence[int],
-                iouv: torch.Tensor) -> torch.Tensor:
+                iouv: torch.Tensor, iouv_host: Optional[Sequence[float]] = None) -> torch.Tensor:
     """Batched GPU form of the reference's ``process_batch`` (val.py:32-54): ``dets [B, max_det, 6]`` /
     ``counts [B]`` of one task in native image space, ``labels [sum M_b, 5]`` (cls, x1, y1, x2, y2) with
     ``label_offsets`` (``B+1`` python ints) -> ``correct [B, max_det, K]`` bool (device)."""
@@ -372,7 +477,7 @@ def match_batch(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, 
     dets, counts = dets.contiguous().float(), counts.contiguous().to(torch.int32)
     labels = labels.to(device=dev, dtype=torch.float32).contiguous()
     offs_d = torch.tensor(offs, dtype=torch.int32, device=dev)
-    iou_host = [float(v) for v in iouv.detach().cpu().float().tolist()]
+    iou_host = list(iouv_host) if iouv_host is not None else [float(v) for v in iouv.detach().cpu().float().tolist()]
     K = len(iou_host)
     correct = torch.empty((B, max_det, K), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

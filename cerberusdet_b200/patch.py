@@ -9,7 +9,13 @@ What gets rebound (and restored by ``uninstall()``):
   detect.py:18, cerberusdet_inference.py:10);
 * ``cerberusdet.cerberusdet_inference.CerberusDetInference`` -> ``inference.CerberusDetInference``;
 * with ``train=True`` also ``cerberusdet.utils.loss.Loss.bbox_decode`` -> ``ops.bbox_decode`` (the training-time
-  sibling of the decode, reference utils/loss.py:126-131; forward and backward kernels).
+  sibling of the decode, reference utils/loss.py:126-131; forward and backward kernels).  The reference's trainer
+  computes the loss under ``amp.autocast`` (trainers/averaging.py:158): there ``softmax`` runs in fp32 on the fp16
+  ``pred_dist``, autocast rounds its output to fp16 for the ``matmul`` with ``proj`` (fp32 accumulation, fp16 result) and
+  ``dist2bbox`` stays in fp16 -- exactly the half path of the kernels (probabilities rounded to half, one rounding of
+  the expectation, one per corner), so fp16 ``pred_dist`` + fp16 anchors under autocast go to the kernels; any other
+  dtype mix (fp32 under autocast, anchors of another dtype) keeps the reference's own code;
+* with ``val=True`` the validation loop's per-image matching (val.py:32-54 ``process_batch``) -> ``ops.match_batch``.
 
 CUDA fp16/fp32 tensors go to the kernels; anything else (CPU tensors, training mode, masks/labels
 arguments) is handed to the reference's own, saved implementation -- the patch never changes what a
@@ -34,13 +40,13 @@ def installed() -> bool:
     return bool(_saved)
 
 
-def install(import_all: bool = False, train: bool = False) -> Dict[str, List[str]]:
+def install(import_all: bool = False, train: bool = False, val: bool = False) -> Dict[str, List[str]]:
     """Patch the reference modules that are importable.  ``import_all`` also imports ``val`` /
     ``detect`` / ``cerberusdet_inference`` (they pull in the whole data pipeline); by default only
     modules already imported, plus ``models.yolo`` and ``utils.general``, are touched.  ``train`` also rebinds
-    ``Loss.bbox_decode`` (imports ``cerberusdet.utils.loss``)."""
-    if _saved:
-        return {"already": ["installed"]}
+    ``Loss.bbox_decode`` (imports ``cerberusdet.utils.loss``), ``val`` the validation matching (imports
+    ``cerberusdet.val``).  Calling it again adds whatever is not patched yet (e.g. ``install()`` then
+    ``install(train=True)``)."""
     import torch
 
     from . import detect as _detect
@@ -48,57 +54,82 @@ def install(import_all: bool = False, train: bool = False) -> Dict[str, List[str
     from . import nms as _nms
 
     done: Dict[str, List[str]] = {"patched": []}
+    already = {(id(obj), name) for obj, name, _ in _saved}
+
+    def patch_once(obj, name, value, label):
+        if (id(obj), name) in already:
+            return
+        _set(obj, name, value)
+        already.add((id(obj), name))
+        done["patched"].append(label)
+
     yolo = importlib.import_module("cerberusdet.models.yolo")
     general = importlib.import_module("cerberusdet.utils.general")
 
     det_cls = yolo.Detect
     if not hasattr(det_cls, "_cerb_reference_forward"):
         det_cls._cerb_reference_forward = det_cls.forward
-    _set(det_cls, "forward", _detect.detect_forward)
-    done["patched"].append("cerberusdet.models.yolo.Detect.forward")
+    patch_once(det_cls, "forward", _detect.detect_forward, "cerberusdet.models.yolo.Detect.forward")
 
-    reference_nms = general.non_max_suppression
+    cur = general.non_max_suppression
+    if hasattr(cur, "_cerb_reference"):
+        non_max_suppression = cur  # already ours: reuse the same wrapper for late-imported modules
+    else:
+        reference_nms = cur
 
-    def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
-                            multi_label=False, labels=(), max_det=300, nm=0):
-        p = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
-        on_path = p.is_cuda and p.dtype in (torch.float16, torch.float32) and not nm and not (labels is not None and len(labels))
-        if not on_path:
-            return reference_nms(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, max_det, nm)
-        return _nms.non_max_suppression(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, max_det, nm)
+        def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                                multi_label=False, labels=(), max_det=300, nm=0):
+            p = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
+            on_path = p.is_cuda and p.dtype in (torch.float16, torch.float32) and not nm and not (labels is not None and len(labels))
+            if not on_path:
+                return reference_nms(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, max_det, nm)
+            return _nms.non_max_suppression(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, max_det, nm)
 
-    non_max_suppression.__doc__ = _nms.non_max_suppression.__doc__
-    non_max_suppression._cerb_reference = reference_nms
+        non_max_suppression.__doc__ = _nms.non_max_suppression.__doc__
+        non_max_suppression._cerb_reference = reference_nms
     for modname in _NMS_IMPORTERS:
         mod = sys.modules.get(modname)
-        if mod is None and (import_all or modname == "cerberusdet.utils.general"):
+        if mod is None and (import_all or modname == "cerberusdet.utils.general" or (val and modname == "cerberusdet.val")):
             mod = importlib.import_module(modname)
         if mod is not None and hasattr(mod, "non_max_suppression"):
-            _set(mod, "non_max_suppression", non_max_suppression)
-            done["patched"].append(f"{modname}.non_max_suppression")
+            patch_once(mod, "non_max_suppression", non_max_suppression, f"{modname}.non_max_suppression")
 
     inf = sys.modules.get("cerberusdet.cerberusdet_inference")
     if inf is None and import_all:
         inf = importlib.import_module("cerberusdet.cerberusdet_inference")
     if inf is not None:
-        _set(inf, "CerberusDetInference", _inference.CerberusDetInference)
-        done["patched"].append("cerberusdet.cerberusdet_inference.CerberusDetInference")
+        patch_once(inf, "CerberusDetInference", _inference.CerberusDetInference,
+                   "cerberusdet.cerberusdet_inference.CerberusDetInference")
     if train:
         from . import ops as _ops
 
         loss_mod = importlib.import_module("cerberusdet.utils.loss")
-        reference_bbox_decode = loss_mod.Loss.bbox_decode
+        if not hasattr(loss_mod.Loss.bbox_decode, "_cerb_reference"):
+            reference_bbox_decode = loss_mod.Loss.bbox_decode
 
-        def bbox_decode(self, anchor_points, pred_dist):
-            on_path = (self.use_dfl and pred_dist.is_cuda and pred_dist.dtype in (torch.float16, torch.float32)
-                       and pred_dist.dim() == 3 and pred_dist.shape[-1] == 64 and not torch.is_autocast_enabled())
-            if not on_path:  # CPU tensors, reg_max != 16, autocast (its softmax/matmul casts are the reference's business)
-                return reference_bbox_decode(self, anchor_points, pred_dist)
-            return _ops.bbox_decode(anchor_points, pred_dist)
+            def bbox_decode(self, anchor_points, pred_dist):
+                on_path = (self.use_dfl and pred_dist.is_cuda and pred_dist.dim() == 3 and pred_dist.shape[-1] == 64
+                           and anchor_points.dtype == pred_dist.dtype)
+                if on_path and torch.is_autocast_enabled():
+                    # autocast: fp32 softmax -> fp16 probabilities -> fp16 matmul (fp32 accumulate): the kernels' half path
+                    on_path = pred_dist.dtype == torch.float16 and torch.get_autocast_gpu_dtype() == torch.float16
+                elif on_path:
+                    on_path = pred_dist.dtype in (torch.float16, torch.float32)
+                if not on_path:  # CPU tensors, reg_max != 16, mixed dtypes: the reference's own code
+                    return reference_bbox_decode(self, anchor_points, pred_dist)
+                return _ops.bbox_decode(anchor_points, pred_dist)
 
-        bbox_decode._cerb_reference = reference_bbox_decode
-        _set(loss_mod.Loss, "bbox_decode", bbox_decode)
-        done["patched"].append("cerberusdet.utils.loss.Loss.bbox_decode")
+            bbox_decode._cerb_reference = reference_bbox_decode
+            patch_once(loss_mod.Loss, "bbox_decode", bbox_decode, "cerberusdet.utils.loss.Loss.bbox_decode")
+    if val:
+        from . import val_stats as _val_stats
+
+        val_mod = importlib.import_module("cerberusdet.val")
+        if not hasattr(val_mod.process_batch, "_cerb_reference"):
+            patch_once(val_mod, "process_batch", _val_stats.make_process_batch(val_mod.process_batch),
+                       "cerberusdet.val.process_batch")
+    if not done["patched"]:
+        return {"already": ["installed"]}
     return done
 
 

@@ -38,3 +38,46 @@ def match_predictions(detections: torch.Tensor, labels: torch.Tensor, iouv: torc
                     taken.add(l)
                     correct[d, i] = True
     return correct
+
+
+def make_process_batch(reference_process_batch):
+    """Drop-in for the reference's ``process_batch(detections, labels, iouv)`` (cerberusdet/val.py:32-54), bound onto
+    ``cerberusdet.val`` by ``patch.install(val=True)``: the validation loop (val.py:321-357) calls it once per image.
+    CUDA tensors go to ``cerb_val_match`` (ONE launch and no host round trip per image, where the reference makes
+    ~5 launches and a ``.cpu().numpy()`` sync per IoU threshold -- 10 of them); anything else (CPU tensors, more than
+    1024 labels or detections in an image) runs the reference's own function."""
+    from . import ops
+
+    cache = {}
+
+    def process_batch(detections, labels, iouv):
+        n, m = int(detections.shape[0]), int(labels.shape[0])
+        on_path = (detections.is_cuda and labels.is_cuda and detections.dim() == 2 and detections.shape[1] == 6
+                   and labels.dim() == 2 and labels.shape[1] == 5 and 0 < n <= 30000 and 0 < m <= 1024)
+        if not on_path:
+            return reference_process_batch(detections, labels, iouv)
+        key = (iouv.data_ptr(), int(iouv.shape[0]), getattr(iouv, "_version", 0))
+        host = cache.get(key)
+        if host is None:  # the thresholds are one tensor for the whole run (val.py:206): read them once
+            cache.clear()
+            host = cache[key] = [float(v) for v in iouv.detach().cpu().float().tolist()]
+        counts = torch.full((1,), n, dtype=torch.int32, device=detections.device)
+        correct = ops.match_batch(detections.float().unsqueeze(0), counts, labels, [0, m], iouv, iouv_host=host)
+        return correct[0]
+
+    process_batch._cerb_reference = reference_process_batch
+    return process_batch
+
+
+def batch_statistics(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, label_offsets, iouv: torch.Tensor):
+    """The whole statistics step of one validation batch and one task in a single launch: ``dets [B, max_det, 6]`` /
+    ``counts [B]`` straight from ``ops.nms_batched`` (already in native space, see ``ops.cross_task_merge``'s ``scale`` or
+    the reference's ``scale_boxes``), ``labels [sum M_b, 5]`` native-space rows with ``label_offsets [B+1]``.
+    Returns ``(correct [sum n_b, K] bool, conf [sum n_b], pcls [sum n_b])`` concatenated over the images in order -- the
+    first three columns the reference appends to ``stats`` per image (val.py:357) -- as device tensors."""
+    from . import ops
+
+    correct = ops.match_batch(dets, counts, labels, label_offsets, iouv)  # [B, max_det, K]
+    n = counts.to(torch.int64)
+    keep = torch.arange(dets.shape[1], device=dets.device)[None, :] < n[:, None]  # rows below each image's count
+    return correct[keep], dets[..., 4][keep], dets[..., 5][keep]

@@ -14,7 +14,7 @@
  *    pointer after the call returns.
  *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call
  *    synchronises the device.  Re-entrant; safe from several host threads on
- *    different streams.
+ *    different streams: the only mutable state (last error, test knobs) is thread-local.
  *  - Return 0 on success, a negative CERB_E* code otherwise; cerb_last_error() gives the
  *    calling thread's message.  There is no CPU fallback.
  *  - dtype: CERB_F16 (IEEE half) or CERB_F32; tensors are contiguous.
@@ -182,6 +182,17 @@ int cerb_bbox_decode_fwd(const void* pred_dist, const void* anchor_points, long 
  */
 int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_rows, int reg_max, int dtype,
                          void* grad_pred_dist, void* stream);
+
+/*
+ * Test / tools hooks.  cerb_debug_set(name, value) overrides one internal choice FOR THE CALLING THREAD (so the
+ * library stays re-entrant); cerb_debug_reset() drops every override of the calling thread.  Results never depend
+ * on a knob: the parity tests run the alternatives against each other.  Knobs: "decode_pipe" (0 = register-resident
+ * decode kernel instead of the pipelined one), "decode_order", "decode_vec", "decode_l2hint", "nms_minb" (1 | 2: the
+ * 128- / 64-register NMS build), "nms_pdl" (0 = no programmatic dependent launch), "chunk_cap", "chunk_first",
+ * "hist_sample".
+ */
+int cerb_debug_set(const char* name, int value);
+int cerb_debug_reset(void);
 
 /*
  * Test hook: override the chunk capacity (16..4096) and first-chunk target of the lazy

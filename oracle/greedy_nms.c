@@ -22,7 +22,16 @@
 static inline float fmax_std(float a, float b) { return (a < b) ? b : a; } /* std::max */
 static inline float fmin_std(float a, float b) { return (b < a) ? b : a; } /* std::min */
 
+/* max_keep > 0: stop as soon as max_keep boxes are kept.  Greedy suppression is causal (whether box i is kept depends
+ * only on boxes before it), so the first max_keep entries are exactly those of the full run -- the caller cuts the
+ * list there anyway (reference general.py:465 `i = i[:max_det]`); it only spares the O(n^2) tail. */
+long oracle_greedy_nms_topk(const float *boxes, long n, double iou_threshold, long *keep, long max_keep);
+
 long oracle_greedy_nms(const float *boxes, long n, double iou_threshold, long *keep) {
+    return oracle_greedy_nms_topk(boxes, n, iou_threshold, keep, 0);
+}
+
+long oracle_greedy_nms_topk(const float *boxes, long n, double iou_threshold, long *keep, long max_keep) {
     if (n <= 0) return 0;
     unsigned char *dead = (unsigned char *)calloc((size_t)n, 1);
     float *area = (float *)malloc(sizeof(float) * (size_t)n);
@@ -34,6 +43,7 @@ long oracle_greedy_nms(const float *boxes, long n, double iou_threshold, long *k
     for (long i = 0; i < n; ++i) {
         if (dead[i]) continue;
         keep[kept++] = i;
+        if (max_keep > 0 && kept >= max_keep) break;
         const float ix1 = boxes[4 * i], iy1 = boxes[4 * i + 1];
         const float ix2 = boxes[4 * i + 2], iy2 = boxes[4 * i + 3];
         const float ia = area[i];

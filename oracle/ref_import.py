@@ -1,10 +1,11 @@
 """Import the UNMODIFIED reference (ai-forever/CerberusDet) in this container.
 
 TEST INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` to produce the golden
-vectors under ``tests/golden/`` and by the container-only tests that validate the
-oracle restatement against the real reference.  ``/root/reference`` does not exist
-on the GPU box, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may
-call this module.
+vectors under ``tests/golden/`` and by the tests that validate the oracle restatement and
+the drop-in against the real reference.  ``/root/reference`` does not exist on the GPU box;
+there the same files are found under ``oracle/_ref`` (``oracle/make_ref.py``, git-ignored, shipped
+with the snapshot), so the ``-m gpu`` drop-in tests and ``bench.py``'s reference legs run the
+reference itself and never read ``/root/reference``.
 
 The reference's hot-path modules import plotting/logging packages at module import
 time (``utils/general.py:20`` -> ``utils/metrics.py:9`` -> matplotlib;
@@ -18,7 +19,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CERB_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """``/root/reference`` in the build container; on the GPU box the file-for-file copy ``oracle/_ref`` that
+    ``oracle/make_ref.py`` ships with the snapshot (git-ignored)."""
+    env = os.environ.get("CERB_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/cerberusdet"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

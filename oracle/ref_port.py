@@ -70,16 +70,19 @@ def _c():
             ctypes.c_double,  # iou threshold
             ctypes.c_void_p,  # long* keep [n]
         ]
+        lib.oracle_greedy_nms_topk.restype = ctypes.c_long
+        lib.oracle_greedy_nms_topk.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_void_p, ctypes.c_long]
         _lib = lib
     return _lib
 
 
-def greedy_nms_c(boxes: torch.Tensor, iou_thres: float) -> torch.Tensor:
-    """Greedy suppression over boxes ALREADY in processing order (score-descending)."""
+def greedy_nms_c(boxes: torch.Tensor, iou_thres: float, max_keep: int = 0) -> torch.Tensor:
+    """Greedy suppression over boxes ALREADY in processing order (score-descending).  ``max_keep > 0`` stops after that
+    many kept boxes (the same first ``max_keep`` indices as the full run: greedy suppression is causal)."""
     b = np.ascontiguousarray(boxes.detach().cpu().numpy(), dtype=np.float32)
     n = b.shape[0]
     keep = np.empty(max(n, 1), dtype=np.int64)
-    k = _c().oracle_greedy_nms(b.ctypes.data, n, float(iou_thres), keep.ctypes.data)
+    k = _c().oracle_greedy_nms_topk(b.ctypes.data, n, float(iou_thres), keep.ctypes.data, int(max_keep))
     return torch.from_numpy(keep[:k].copy())
 
 
@@ -216,7 +219,7 @@ def nms_port(
 
                 keep = torchvision.ops.nms(shifted, det[:, 4], iou_thres)  # :464
             else:
-                keep = greedy_nms_c(shifted, iou_thres)
+                keep = greedy_nms_c(shifted, iou_thres, max_keep=max_det)  # early exit: same first max_det indices
             det_out = det[keep[:max_det]]  # :465,474
         else:
             det_out = det

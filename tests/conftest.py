@@ -43,3 +43,13 @@ def split_rows(rows, counts):
         out.append(torch.from_numpy(rows[o : o + c].copy()))
         o += c
     return out
+
+
+@pytest.fixture()
+def knobs():
+    """Set thread-local test knobs of libcerb_post.so (include/cerb_post.h: cerb_debug_set); all are dropped afterwards."""
+    from cerberusdet_b200 import _lib
+
+    _lib.debug_reset()
+    yield _lib.debug_set
+    _lib.debug_reset()

@@ -56,20 +56,19 @@ def test_decode_vs_oracle_multitask(ops, dtype, imgsz, bsz):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
-@pytest.mark.parametrize("ipt", [1, 2, 4])
-def test_decode_pipelined_kernel_bit_identical_to_register_kernel(ops, dtype, ipt, monkeypatch):
-    """decode_pipe.cu (cp.async prefetch, ipt items per thread) and decode.cu do the same arithmetic: y and the score
-    summary must be bit-identical, on ragged item counts (B * hw / VEC not a multiple of 128 * ipt), several class
+def test_decode_pipelined_kernel_bit_identical_to_register_kernel(ops, dtype, knobs):
+    """decode_pipe.cu (cp.async prefetch, several items per thread) and decode.cu do the same arithmetic: y and the score
+    summary must be bit-identical, on ragged item counts (B * hw / VEC not a multiple of the items per CTA), several class
     group remainders (nc % 4 = 0, 3, 1, 2) and more than one class group ring turn (nc = 80)."""
     from cerberusdet_b200 import ops as o
 
     for ncs, imgsz, bsz in [([20, 19, 12], (640, 640), 3), ([80, 5, 1, 2], (96, 72), 5), ([19], (1280, 736), 1)]:
         heads = synth_heads(range(bsz), ncs, imgsz, dtype, "iid", cfg=77)
         dev = [[_dev(x) for x in lv] for lv in heads]
-        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", "0")
+        knobs("decode_pipe", 0)
         y0 = ops.decode_heads(dev, STRIDES)
         s0 = [o.find_summary(y) for y in y0]
-        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", str(ipt))
+        knobs("decode_pipe", 1)
         y1 = ops.decode_heads(dev, STRIDES)
         s1 = [o.find_summary(y) for y in y1]
         for t in range(len(ncs)):
@@ -90,14 +89,14 @@ def test_decode_pipelined_kernel_bit_identical_to_register_kernel(ops, dtype, ip
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
 @pytest.mark.parametrize("pipe", ["0", "default"])
-def test_decode_split_heads_bit_identical_to_concatenated(ops, dtype, pipe, monkeypatch):
+def test_decode_split_heads_bit_identical_to_concatenated(ops, dtype, pipe, knobs):
     """cerb_decode_split reads the box channels (cv2 output) and the class channels (cv3 output) from their own tensors
     -- the concat of reference models/yolo.py:89-90 is never made -- and must give the same bits as cerb_decode on the
     concatenated tensors, through both kernels and on the scalar (unaligned) path."""
     from cerberusdet_b200 import ops as o
 
     if pipe != "default":
-        monkeypatch.setenv("CERB_DEBUG_DECODE_PIPE", pipe)
+        knobs("decode_pipe", int(pipe))
     for ncs, imgsz, bsz, strides in [([20, 19, 12], (640, 640), 2, STRIDES), ([80, 3], (96, 72), 3, STRIDES), ([5], (40, 24), 2, (8.0,))]:
         heads = synth_heads(range(bsz), ncs, imgsz, dtype, "iid", cfg=55, strides=strides)
         dev = [[_dev(x) for x in lv] for lv in heads]
@@ -140,13 +139,13 @@ def _assert_rows_equal(got, want, ctx=""):
 @pytest.mark.parametrize("minb", [1, 2])
 @pytest.mark.parametrize("chunking", [(0, 0), (16, 1), (64, 7), (300, 300)])
 @pytest.mark.parametrize("name", golden_names("nms"))
-def test_nms_golden_bit_exact(ops, name, chunking, minb, monkeypatch):
+def test_nms_golden_bit_exact(ops, name, chunking, minb, knobs):
     """Every golden vector through both register builds of the NMS kernel (minb 1: 128 registers, used when each segment
     gets its own SM; minb 2: 64 registers, two CTAs per SM) and four chunking settings."""
     from cerberusdet_b200 import _lib
     from cerberusdet_b200.nms import non_max_suppression
 
-    monkeypatch.setenv("CERB_DEBUG_NMS_MINB", str(minb))
+    knobs("nms_minb", minb)
     g = load_golden(name)
     if chunking != (0, 0) and g["pred"].shape[2] > 4000 and chunking[0] < 300:
         pytest.skip("tiny chunks on the large vectors only repeat the same paths slowly")
@@ -176,11 +175,11 @@ CASES = [
 
 @pytest.mark.parametrize("minb", [1, 2])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_nms_vs_oracle(ops, case, minb, monkeypatch):
+def test_nms_vs_oracle(ops, case, minb, knobs):
     from cerberusdet_b200.nms import non_max_suppression
     from oracle import ref_port as rp
 
-    monkeypatch.setenv("CERB_DEBUG_NMS_MINB", str(minb))
+    knobs("nms_minb", minb)
     bsz, nc, anchors, dtype, regime, kw = CASES[case]
     pred = synth_prediction(bsz, nc, anchors, seed=100 + case, dtype=dtype, regime=regime)
     want = rp.nms_port(pred, greedy="c", **kw)
@@ -368,10 +367,16 @@ def test_full_size_properties_cfg3(ops):
     ys_shard = [y[16:32].contiguous() for y in ys]
     d2, c2 = ops.nms_batched(ys_shard, **kw)
     assert torch.equal(c2, counts[:, 16:32]) and torch.equal(d2, dets[:, 16:32])
-    # spot check against the oracle fed the SAME decoded tensor (selection must be bit exact)
-    for (t, b) in [(0, 0), (1, 17), (2, 63)]:
-        want = rp.nms_port(ys[t][b : b + 1].cpu(), greedy="c", **kw)[0]
-        assert torch.equal(dets[t, b, : counts_h[t, b]].cpu(), want)
+    # EVERY one of the 192 segments against the oracle fed the SAME decoded tensor (selection must be bit exact)
+    dets_h = dets.cpu()
+    for t in range(3):
+        want = rp.nms_port(ys[t].cpu(), greedy="c", **kw)
+        for b in range(bsz):
+            assert torch.equal(dets_h[t, b, : counts_h[t, b]], want[b]), f"segment task {t} image {b}"
+    # and the decode itself, every image, within the north_star tolerance of the oracle port
+    for t, nc in enumerate(ncs):
+        ok, msg = check_decode(ys[t], rp.decode_port(heads[t], nc, STRIDES), level_shapes(640, STRIDES), STRIDES, nc)
+        assert ok, f"task {t}: {msg}"
 
 
 # ------------------------------------------------------------------ shapes beyond the BASELINE configs
@@ -401,7 +406,7 @@ def test_decode_and_nms_other_head_shapes(ops, dtype, nc, imgsz, strides, bsz):
 
 def test_full_size_cfg2_and_cfg4(ops):
     """BASELINE configs 2 (B=32, 2 tasks, best class, conf 0.3) and 4 (B=16, 1280^2, 33600 anchors, multi-label) at
-    full size: properties on every segment + bit-exact spot checks against the oracle."""
+    full size: properties on every segment and EVERY segment bit-exact against the oracle fed the same decoded tensor."""
     from oracle import ref_port as rp
 
     for ncs, bsz, imgsz, kw in (([20, 19], 32, 640, dict(conf_thres=0.3, iou_thres=0.45, max_det=300)),
@@ -417,9 +422,11 @@ def test_full_size_cfg2_and_cfg4(ops):
                 n = int(ch[t, b])
                 assert (s[t, b, : n - 1] >= s[t, b, 1:n]).all()
                 assert (dets[t, b, n:] == 0).all()          # padding rows are zeroed by the kernel
-        for (t, b) in [(0, 0), (len(ncs) - 1, bsz - 1)]:
-            want = rp.nms_port(ys[t][b : b + 1].cpu(), greedy="c", **kw)[0]
-            assert torch.equal(dets[t, b, : int(ch[t, b])].cpu(), want)
+        dets_h = dets.cpu()
+        for t in range(len(ncs)):
+            want = rp.nms_port(ys[t].cpu(), greedy="c", **kw)
+            for b in range(bsz):
+                assert torch.equal(dets_h[t, b, : int(ch[t, b])], want[b]), f"imgsz {imgsz} segment task {t} image {b}"
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])

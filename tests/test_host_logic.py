@@ -10,7 +10,10 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.path.isdir("/root/reference/cerberusdet")
+sys.path.insert(0, ROOT)
+from oracle.ref_import import reference_available  # noqa: E402
+
+REF = reference_available()  # /root/reference in the build container, oracle/_ref (oracle/make_ref.py) on the GPU box
 
 
 def test_shared_library_exports_every_declared_symbol():
@@ -146,7 +149,7 @@ def _random_dets(gen, n, ncls_total, clustered=True):
     return det
 
 
-@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
 def test_cross_task_tail_matches_reference():
     from cerberusdet_b200 import cross_task as ct
     from oracle.ref_import import load_reference
@@ -171,7 +174,7 @@ def test_cross_task_tail_matches_reference():
             assert torch.equal(i1, ct.pairwise_iou(det[:7, :4], det[3:, :4]))
 
 
-@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
 def test_patch_install_rebinds_and_restores():
     from cerberusdet_b200 import patch
     from oracle.ref_import import load_reference
@@ -204,7 +207,7 @@ def test_patch_install_rebinds_and_restores():
     assert ref.yolo.Detect.forward is orig_fwd and ref.general.non_max_suppression is orig_nms
 
 
-@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
 def test_patch_install_train_rebinds_bbox_decode_and_keeps_cpu_results():
     import types
 
@@ -224,6 +227,53 @@ def test_patch_install_train_rebinds_bbox_decode_and_keeps_cpu_results():
     finally:
         patch.uninstall()
     assert loss_mod.Loss.bbox_decode is orig
+
+
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
+def test_patched_inference_class_keeps_cpu_models_working(tmp_path, monkeypatch):
+    """after install() a device='cpu' CerberusDetInference must still work (the reference's own NMS runs)."""
+    import copy
+    import warnings
+
+    from cerberusdet_b200 import patch
+    from oracle.ref_import import REFERENCE_ROOT, load_reference
+
+    monkeypatch.setenv("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")  # attempt_load unpickles whole modules (torch >= 2.6)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", ""))  # select_device('cpu') rewrites it
+    load_reference()
+    import cerberusdet.cerberusdet_inference as inf_mod
+    import cerberusdet.models.cerberus as cerb_mod
+
+    patch.uninstall()
+
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # a narrow copy of the config keeps the CPU forward fast
+        import yaml
+
+        with open(os.path.join(REFERENCE_ROOT, "cerberusdet/models/yolov8x_voc_obj365.yaml")) as f:
+            cfg = yaml.safe_load(f)
+        cfg["width_multiple"], cfg["depth_multiple"] = 0.125, 0.33
+        model = cerb_mod.CerberusDet(task_ids=["voc", "objects365_animals"], nc=[20, 19], cfg=cfg, ch=3, verbose=False)
+        model.sequential_split(copy.deepcopy(model.yaml["cerber"]), "cpu")
+        for m in model.modules():
+            if type(m).__name__ == "Detect":
+                for seq in m.cv3:
+                    seq[-1].bias.data.fill_(-2.0)
+        model.names = {"voc": [f"voc{i}" for i in range(20)], "objects365_animals": [f"ani{i}" for i in range(19)]}
+        path = os.path.join(str(tmp_path), "small.pt")
+        torch.save({"model": model}, path)
+        img = torch.rand(1, 3, 128, 128)
+        ref_eng = inf_mod.CerberusDetInference(path, device="cpu", conf_thres=0.1, img_size=128)
+        want = ref_eng.predict(img)
+        patch.install(import_all=True)
+        eng = inf_mod.CerberusDetInference(path, device="cpu", conf_thres=0.1, img_size=128)
+        got = eng.predict(img)
+    assert type(eng).__module__ == "cerberusdet_b200.inference"
+    assert got == want and len(want[0]) > 0
+    patch.uninstall()
+    assert inf_mod.CerberusDetInference is not type(eng)
 
 
 _WORKER2 = r"""
@@ -281,7 +331,7 @@ def _val_case(g, M, N, ncls=4):
     return det, lab
 
 
-@pytest.mark.skipif(not REF, reason="needs /root/reference (build container only)")
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
 def test_val_matching_matches_reference_process_batch():
     """val_stats.match_predictions == the reference's process_batch (cerberusdet/val.py:32-54)."""
     from oracle.ref_import import load_reference

@@ -1,5 +1,6 @@
-"""Container-only: the oracle restatement against the UNMODIFIED reference on fresh random inputs (beyond the committed
-golden vectors).  Needs /root/reference, so these tests are skipped on the GPU box."""
+"""The oracle restatement against the UNMODIFIED reference on fresh random inputs (beyond the committed golden vectors).
+Needs the reference tree: /root/reference in the build container, its file-for-file copy oracle/_ref (oracle/make_ref.py)
+anywhere else."""
 import os
 import sys
 import types
@@ -13,7 +14,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_port as rp  # noqa: E402
 from oracle.ref_import import reference_available  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+pytestmark = pytest.mark.skipif(not reference_available(), reason="needs the reference tree (/root/reference or oracle/_ref)")
 
 
 @pytest.fixture(scope="module")
