@@ -22,8 +22,11 @@ EXPORTS = (
     "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
+    "cerb_nms_stats",
     "cerb_decode_nms",
     "cerb_cross_task",
+    "cerb_cross_task_workspace_bytes",
+    "cerb_cross_task_ws",
     "cerb_val_match",
     "cerb_bbox_decode_fwd",
     "cerb_bbox_decode_bwd",
@@ -67,10 +70,18 @@ def load() -> ctypes.CDLL:
     lib.cerb_nms_workspace_bytes.argtypes = [i, i, i]
     lib.cerb_nms.restype = i
     lib.cerb_nms.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp]
+    if hasattr(lib, "cerb_nms_stats") or "CERB_LIB" not in os.environ:
+        lib.cerb_nms_stats.restype = i
+        lib.cerb_nms_stats.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp, vp]
     lib.cerb_decode_nms.restype = i
     lib.cerb_decode_nms.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_cross_task.restype = i
     lib.cerb_cross_task.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp]
+    if hasattr(lib, "cerb_cross_task_ws") or "CERB_LIB" not in os.environ:
+        lib.cerb_cross_task_workspace_bytes.restype = sz
+        lib.cerb_cross_task_workspace_bytes.argtypes = [i, i, i]
+        lib.cerb_cross_task_ws.restype = i
+        lib.cerb_cross_task_ws.argtypes = [vp, vp, i, i, i, ip, d, vp, vp, vp, vp, sz, vp]
     lib.cerb_val_match.restype = i
     lib.cerb_val_match.argtypes = [vp, vp, i, i, vp, vp, i, fp, i, vp, vp]
     lg = ctypes.c_long

@@ -240,6 +240,14 @@ static float iou_threshold_as_float(double thr) {
 extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                         double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
                         int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+    return cerb_nms_stats(pred, nc, T, B, A, dtype, conf_thres, iou_thres, classes, n_classes, agnostic, multi_label, max_det,
+                          max_nms, max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+                              double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
+                              int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts,
+                              void* workspace, size_t workspace_bytes, unsigned long long* stats, void* stream) {
     g_err[0] = 0;
     REQUIRE(pred && nc, "cerb_nms: null argument");
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_nms: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
@@ -288,6 +296,7 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
     P.max_nms = max_nms;
     P.dets = dets;
     P.counts = counts;
+    P.pair_counts = stats;
     const size_t need = cerb_nms_kept_ws_bytes(T, B, max_det);
     if (need) {
         if (workspace == nullptr || workspace_bytes < need) {
@@ -332,26 +341,45 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
     return 0;
 }
 
-extern "C" int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
-                               double iou_thres, const float* scale, float* out, int* out_counts, void* stream) {
+extern "C" size_t cerb_cross_task_workspace_bytes(int T, int B, int max_det) {
+    if (T <= 0 || B <= 0 || max_det <= 0) return 0;
+    return cerb_cross_task_ws_bytes(T, B, max_det);
+}
+
+extern "C" int cerb_cross_task_ws(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
+                                  double iou_thres, const float* scale, float* out, int* out_counts, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
     g_err[0] = 0;
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_cross_task: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
     REQUIRE(B >= 0 && max_det >= 0, "cerb_cross_task: negative size");
-    REQUIRE((long)T * max_det <= 1024, "cerb_cross_task: T*max_det=%ld exceeds 1024 rows per image", (long)T * max_det);
+    REQUIRE(max_det <= 65535, "cerb_cross_task: max_det=%d exceeds 65535", max_det);
     if (B == 0) return 0;
     REQUIRE(counts && class_offset && out_counts && (dets || max_det == 0) && (out || max_det == 0), "cerb_cross_task: null argument");
+    const size_t need = cerb_cross_task_ws_bytes(T, B, max_det);
+    if (need && (workspace == nullptr || workspace_bytes < need)) {
+        cerb_set_error("cerb_cross_task: T*max_det=%ld rows per image need a workspace of %zu bytes, got %zu", (long)T * max_det, need,
+                       workspace ? workspace_bytes : (size_t)0);
+        return CERB_ENOSPC;
+    }
+    REQUIRE(!need || aligned_to(workspace, 16), "cerb_cross_task: workspace must be 16-byte aligned");
     CrossTaskParams P;
     memset(&P, 0, sizeof(P));
     P.dets = dets; P.counts = counts; P.T = T; P.B = B; P.max_det = max_det;
     for (int t = 0; t < T; ++t) P.class_offset[t] = class_offset[t];
     P.iou_thr = (float)iou_thres;
     P.scale = scale; P.out = out; P.out_counts = out_counts;
+    P.workspace = need ? (unsigned char*)workspace : nullptr;
     cudaError_t e = cerb_launch_cross_task(P, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         cerb_set_error("cerb_cross_task: launch failed: %s", cudaGetErrorString(e));
         return CERB_ECUDA;
     }
     return 0;
+}
+
+extern "C" int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
+                               double iou_thres, const float* scale, float* out, int* out_counts, void* stream) {
+    return cerb_cross_task_ws(dets, counts, T, B, max_det, class_offset, iou_thres, scale, out, out_counts, nullptr, 0, stream);
 }
 
 extern "C" int cerb_decode_nms(const void* const* lvl, const int* nc, int T, int L, int B, const int* H, const int* W,

@@ -52,6 +52,7 @@ struct NmsParams {
     int class_shortcut; // 1 if different-class tame boxes provably never intersect after the offset
     const void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V] from the decode kernel (else null)
     float tame_lo, tame_hi; // the window of "tame" un-offset coordinates, tame_hi - tame_lo == class_gap
+    unsigned long long* pair_counts;  // optional [T*B][2]: IoU tests made, candidates consumed (statistics), else null
     int force_minb;         // host only: 0 = pick the register build per launch, 1 / 2 = force it (tests, tools)
     int pdl;                // host only: launch with programmatic stream serialization (default 1)
 };
@@ -68,8 +69,10 @@ struct CrossTaskParams {
     const float* scale;      // optional [B, 5]: gain, pad_x, pad_y, orig_w, orig_h (scale_boxes + round), else null
     float* out;              // [B, T*max_det, 6] merged rows, global class ids
     int* out_counts;         // [B]
+    unsigned char* workspace;  // global tables for images with more than 1024 rows (cerb_cross_task_ws_bytes), else null
 };
 cudaError_t cerb_launch_cross_task(const CrossTaskParams& P, cudaStream_t stream);
+size_t cerb_cross_task_ws_bytes(int T, int B, int max_det);
 
 // ------------------------------------------------------------------ validation matching
 struct ValMatchParams {

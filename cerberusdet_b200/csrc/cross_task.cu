@@ -16,35 +16,66 @@
 #include "cerb_kernels.h"
 
 #define XT_THREADS 256
-#define XT_MAX_ROWS 1024  // rows per image (T * max_det) the shared-memory bitmask supports
+#define XT_MAX_ROWS 1024  // rows of one image (sum of the tasks' counts) the shared-memory tables hold; images with more
+                          // rows (max_det = 1000 in the reference's detect.py:124) use the caller's global workspace
 
+// per-image tables, in shared memory (n <= XT_MAX_ROWS) or in the global workspace; [rows] each, mask [rows][words]
+struct XtTables {
+    float4* box;
+    float* score;
+    float* area;
+    unsigned short* task;
+    unsigned short* src;   // position inside the task's padded rows
+    unsigned* deleted;     // [words]
+    unsigned* mask;        // [n][words]
+};
+__host__ __device__ inline size_t xt_table_bytes(size_t rows) {
+    const size_t words = (rows + 31) / 32;
+    // box 16, score 4, area 4, task 2, src 2 per row; deleted words; mask rows * words; 16-byte aligned pieces
+    return rows * 28 + ((words * 4 + 15) / 16) * 16 + rows * words * 4 + 64;
+}
+__device__ __forceinline__ XtTables xt_carve(unsigned char* base, size_t rows) {
+    const size_t words = (rows + 31) / 32;
+    XtTables t;
+    t.box = reinterpret_cast<float4*>(base); base += rows * 16;
+    t.score = reinterpret_cast<float*>(base); base += rows * 4;
+    t.area = reinterpret_cast<float*>(base); base += rows * 4;
+    t.task = reinterpret_cast<unsigned short*>(base); base += rows * 2;
+    t.src = reinterpret_cast<unsigned short*>(base); base += rows * 2;
+    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
+    t.deleted = reinterpret_cast<unsigned*>(base); base += ((words * 4 + 15) / 16) * 16;
+    t.mask = reinterpret_cast<unsigned*>(base);
+    return t;
+}
 struct XtSmem {
-    float4 box[XT_MAX_ROWS];
-    float score[XT_MAX_ROWS];
-    float area[XT_MAX_ROWS];
-    unsigned short task[XT_MAX_ROWS];
-    unsigned short src[XT_MAX_ROWS];  // position inside the task's padded rows
-    unsigned deleted[XT_MAX_ROWS / 32];
     int start[CERB_MAX_TASKS + 1];
     int any_overlap;
-    unsigned mask[1];  // [n][words], dynamic
+    int pad[2];
 };
 
 __global__ void __launch_bounds__(XT_THREADS) cross_task_kernel(const __grid_constant__ CrossTaskParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    XtSmem& S = *reinterpret_cast<XtSmem*>(smem_raw);
+    XtSmem& H = *reinterpret_cast<XtSmem*>(smem_raw);
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = P.T, md = P.max_det;
 
     if (tid == 0) {
         int n = 0;
-        for (int t = 0; t < T; ++t) { S.start[t] = n; n += min(max(P.counts[t * P.B + b], 0), md); }
-        S.start[T] = n;
-        S.any_overlap = 0;
+        for (int t = 0; t < T; ++t) { H.start[t] = n; n += min(max(P.counts[t * P.B + b], 0), md); }
+        H.start[T] = n;
+        H.any_overlap = 0;
     }
     __syncthreads();
-    const int n = S.start[T];
+    const int n = H.start[T];
     const int words = (n + 31) >> 5;
+    // the tables: shared memory when this image's rows fit (sized by the launch for min(T * max_det, XT_MAX_ROWS) rows),
+    // else this image's slice of the global workspace (the host guarantees it is there whenever T * max_det > XT_MAX_ROWS)
+    const int smem_rows = min(T * md, XT_MAX_ROWS);
+    const XtTables S_ = (n <= smem_rows)
+                            ? xt_carve(smem_raw + sizeof(XtSmem), (size_t)max(n, 1))
+                            : xt_carve(P.workspace + (size_t)b * xt_table_bytes((size_t)T * md), (size_t)n);
+    struct { float4* box; float* score; float* area; unsigned short* task; unsigned short* src; unsigned* deleted; unsigned* mask; int* start; int& any_overlap; }
+        S = {S_.box, S_.score, S_.area, S_.task, S_.src, S_.deleted, S_.mask, H.start, H.any_overlap};
     // ---- combine: rows in task order (cerberusdet_inference.py:72-83)
     for (int t = 0; t < T; ++t) {
         const int s0 = S.start[t], cnt = S.start[t + 1] - s0;
@@ -59,7 +90,7 @@ __global__ void __launch_bounds__(XT_THREADS) cross_task_kernel(const __grid_con
             S.src[s0 + i] = (unsigned short)i;
         }
     }
-    for (int i = tid; i < XT_MAX_ROWS / 32; i += XT_THREADS) S.deleted[i] = 0;
+    for (int i = tid; i < words; i += XT_THREADS) S.deleted[i] = 0;
     __syncthreads();
 
     // ---- IoU bitmask between boxes of different tasks: bit (r, c) for c in a LATER task  (general.py:509-531)
@@ -159,15 +190,18 @@ __global__ void __launch_bounds__(XT_THREADS) cross_task_kernel(const __grid_con
     if (tid == 0) P.out_counts[b] = keep_all ? n : n - ndel;
 }
 
-size_t cerb_cross_task_smem(int rows) {
-    const size_t words = (size_t)(rows + 31) / 32;
-    return sizeof(XtSmem) + (size_t)rows * words * sizeof(unsigned);
+size_t cerb_cross_task_smem(int rows) { return sizeof(XtSmem) + xt_table_bytes((size_t)(rows < XT_MAX_ROWS ? rows : XT_MAX_ROWS)); }
+
+// bytes of global workspace a launch needs: nothing while every image's rows fit the shared-memory tables for sure
+size_t cerb_cross_task_ws_bytes(int T, int B, int max_det) {
+    const size_t rows = (size_t)T * (size_t)max_det;
+    return rows > XT_MAX_ROWS ? (size_t)B * xt_table_bytes(rows) : 0;
 }
 
 cudaError_t cerb_launch_cross_task(const CrossTaskParams& P, cudaStream_t stream) {
     if (P.B == 0) return cudaSuccess;
     const int rows = P.T * P.max_det;
-    if (rows > XT_MAX_ROWS) return cudaErrorInvalidConfiguration;
+    if (rows > XT_MAX_ROWS && P.workspace == nullptr) return cudaErrorInvalidConfiguration;
     const size_t smem = cerb_cross_task_smem(rows);
     cudaError_t e = cudaFuncSetAttribute(cross_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -80,16 +80,26 @@ extern "C" int cerb_debug_read_block_times(unsigned long long* out, int n) {
 #define BLOCK_T_END
 #endif
 
-// Optional phase timers (-DNMS_PROFILE, tools/ only): block 0 accumulates clock64() deltas per phase.
+// Optional phase timers (-DNMS_PROFILE, tools/ only): thread 0 of EVERY block accumulates clock64() deltas per phase in
+// registers/local memory (no global traffic at the stamps, so short phases are not inflated) and adds them to the global
+// totals once, at the end of the kernel.  g_nms_prof[0..9] phases, [10] blocks, [11] consumed, [12..14] collect sub-steps,
+// [15] fixpoint rounds.
 #ifdef NMS_PROFILE
 __device__ unsigned long long g_nms_prof[16];
-#define PROF_DECL long long prof_t = clock64();
+#define PROF_DECL long long prof_t = clock64(), prof_x = 0; unsigned long long prof_acc[16] = {0};
 #define PROF(slot)                                                        \
     do {                                                                  \
-        if (blockIdx.x == 0 && threadIdx.x == 0) {                        \
+        if (threadIdx.x == 0) {                                           \
             const long long now = clock64();                              \
-            g_nms_prof[slot] += (unsigned long long)(now - prof_t);       \
+            prof_acc[slot] += (unsigned long long)(now - prof_t);         \
             prof_t = now;                                                 \
+        }                                                                 \
+    } while (0)
+#define PROF_FLUSH(consumed_)                                             \
+    do {                                                                  \
+        if (threadIdx.x == 0) {                                           \
+            prof_acc[10] = 1; prof_acc[11] = (consumed_);                 \
+            for (int i_ = 0; i_ < 16; ++i_) if (prof_acc[i_]) atomicAdd(&g_nms_prof[i_], prof_acc[i_]); \
         }                                                                 \
     } while (0)
 extern "C" int cerb_debug_read_profile(unsigned long long* out16, int reset) {
@@ -98,19 +108,12 @@ extern "C" int cerb_debug_read_profile(unsigned long long* out16, int reset) {
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_nms_prof, z, sizeof(z)); }
     return 0;
 }
-__device__ long long g_prof_t;
-#define PROFX(slot)                                                       \
-    do {                                                                  \
-        if (blockIdx.x == 0 && threadIdx.x == 0) {                        \
-            const long long now = clock64();                              \
-            g_nms_prof[slot] += (unsigned long long)(now - g_prof_t);     \
-            g_prof_t = now;                                               \
-        }                                                                 \
-    } while (0)
+#define PROFX(slot) do {} while (0)
 #else
 #define PROF_DECL
 #define PROF(slot) do {} while (0)
 #define PROFX(slot) do {} while (0)
+#define PROF_FLUSH(c) do {} while (0)
 #endif
 
 struct __align__(16) NmsSmem {
@@ -761,6 +764,7 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     unsigned consumed = 0;
     int kept = 0;
     unsigned target = min((unsigned)max(P.chunk_first, 1), cap);
+    unsigned npairs = 0;  // IoU tests made by this thread (reported per segment when P.pair_counts is set)
 
     // -------- consume the sorted chunk in S.keys[0..n) (first `take` entries) ; returns updated kept
     auto consume_chunk = [&](unsigned n, unsigned take) {
@@ -834,10 +838,12 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
             if (!dead && kept > 0) {
                 if (fast) {
                     for (int k = S.khead[cls & (NMS_BUCKETS - 1)]; k >= 0; k = S.knext_s[k]) {
+                        ++npairs;
                         if (suppresses(kbox[k], karea[k], box, area, iou_thr)) { dead = true; break; }
                     }
                 } else {
                     for (int k = 0; k < kept; ++k) {
+                        ++npairs;
                         if (suppresses(kbox[k], karea[k], box, area, iou_thr)) { dead = true; break; }
                     }
                 }
@@ -864,11 +870,17 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
             if (!dead) {
                 if (fast) {
                     for (int i = prev; i >= 0; i = S.tprev[i]) {
-                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
+                        if (!S.tdead[i]) {
+                            ++npairs;
+                            if (suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
+                        }
                     }
                 } else {
                     for (int i = 0; i < tid; ++i) {
-                        if (!S.tdead[i] && suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
+                        if (!S.tdead[i]) {
+                            ++npairs;
+                            if (suppresses(S.tbox[i], S.tarea[i], box, area, iou_thr)) NMS_SETBIT(i);
+                        }
                     }
                 }
             }
@@ -910,7 +922,7 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
                     if (lane == 0) { S.keep32[cur ^ 1][wid] = mine; changed = (mine != K[wid]); }
                     cur ^= 1;
 #ifdef NMS_PROFILE
-                    if (blockIdx.x == 0 && tid == 0) g_nms_prof[15] += 1;  // fixpoint block rounds
+                    if (tid == 0) prof_acc[15] += 1;  // fixpoint block rounds
 #endif
                     if (!__syncthreads_or(changed)) break;
                 }
@@ -954,9 +966,6 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     auto collect = [&](u64 lo, u64 hi) -> unsigned {
         if (tid == 0) S.counter = 0;
         __syncthreads();
-#ifdef NMS_PROFILE
-        if (blockIdx.x == 0 && tid == 0) g_prof_t = clock64();
-#endif
         const unsigned sb_lo = (unsigned)(lo >> 32), sb_hi = (unsigned)((hi - 1) >> 32);
         auto put = [&](unsigned sb, int a, int c) {
             const u64 key = make_key(sb, (unsigned)(a * nc + c));
@@ -1080,12 +1089,24 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     }
 
     if (tid == 0) P.counts[seg] = kept;
+    if (P.pair_counts != nullptr) {  // statistics for bench.py / profiles: IoU tests and candidates consumed, per segment
+        unsigned v = npairs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) S.warp_tot[wid] = v;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long tot = 0;
+            for (int w = 0; w < NMS_THREADS / 32; ++w) tot += S.warp_tot[w];
+            P.pair_counts[2 * seg] = tot;
+            P.pair_counts[2 * seg + 1] = consumed;
+        }
+    }
     // rows past the count are zero so the padded [T, B, max_det, 6] output is deterministic without a separate fill
     for (int i = kept * 6 + tid; i < max_det * 6; i += NMS_THREADS) dets[i] = 0.f;
     PROF(9);  // rest
-#ifdef NMS_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0) { g_nms_prof[10] += 1; g_nms_prof[11] += consumed; }
-#endif
+    PROF_FLUSH(consumed);
     BLOCK_T_END
 }
 

@@ -146,7 +146,7 @@ class CerberusDetInference:
         if original_shape is not None:
             shapes = original_shape if isinstance(original_shape, list) else [original_shape] * bsz
         results = []
-        if on_path and len(tasks) * max_det <= cross_task.GPU_MAX_ROWS:
+        if on_path and max_det <= 65535:
             # 3. cross-task merge + rescale on the GPU (one launch, one CTA per image), then ONE D2H copy
             offsets = [min(self.categories_inds_map[t].values()) if self.categories_inds_map[t] else 0 for t in tasks]
             scale = None
@@ -161,7 +161,7 @@ class CerberusDetInference:
             merged_h, mcounts_h = merged.cpu(), mcounts.cpu()
             per_image = [merged_h[i, : int(mcounts_h[i])] for i in range(bsz)]
         else:
-            # too many rows per image for the shared-memory bitmask: host tail, as in the reference
+            # off-path (CPU model): host tail, as in the reference
             dets_h, counts_h = dets.cpu(), counts.cpu()
             per_image = []
             for i in range(bsz):

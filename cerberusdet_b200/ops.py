@@ -53,7 +53,8 @@ def _summary_len(level_sizes: Sequence[int], elt: int) -> int:
 
 
 def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float],
-                 cls_levels: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+                 cls_levels: Optional[Sequence[torch.Tensor]] = None,
+                 out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """Returns ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``; the score summaries ``smax_t`` are empty
     tensors when the shapes do not allow them (see include/cerb_post.h).  With ``cls_levels`` the heads are split:
     ``levels`` hold the 64 box channels, ``cls_levels`` the class channels (``cerb_decode_split``)."""
@@ -93,12 +94,23 @@ def _decode_impl(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Seq
                 if tuple(c.shape) != (B, nc[t], H[l], W[l]):
                     raise ValueError(f"task {t} level {l}: expected class tensor {(B, nc[t], H[l], W[l])}, got {tuple(c.shape)}")
                 cl.append(_dense16(c))
-    ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
     # the score summary exists exactly when every level allows 16-byte vectors (inputs and outputs here are 16-byte
     # aligned by construction), so its shape is a function of the shapes alone -- the fake kernel below relies on that
     R = _summary_len([h * w for h, w in zip(H, W)], first.element_size())
     assert R == 0 or R == int(lib.cerb_summary_row_len(A, code))
-    sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
+    if out is None:
+        ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
+        sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
+    else:  # caller-provided static buffers [y_0 .. y_{T-1}, smax_0 .. smax_{T-1}] (CUDA graphs, pipelines)
+        if len(out) != 2 * T:
+            raise ValueError("out= must hold T prediction buffers followed by T score-summary buffers")
+        ys, sm = list(out[:T]), list(out[T:])
+        for t in range(T):
+            ok = (tuple(ys[t].shape) == (B, 4 + nc[t], A) and tuple(sm[t].shape) == (B, nc[t], R)
+                  and all(z.dtype == first.dtype and z.device == first.device and z.is_contiguous() and z.data_ptr() % 16 == 0
+                          for z in (ys[t], sm[t])))
+            if not ok:
+                raise ValueError(f"out= buffers of task {t} must be contiguous, 16-byte aligned [B,4+nc,A] / [B,nc,{R}] {first.dtype} tensors")
     written = ctypes.c_int(0)
     tail = (_lib.int_array(list(nc)), T, L, B, _lib.int_array(H), _lib.int_array(W),
             _lib.float_array([float(s) for s in strides]), code, _lib.ptr_array([y.data_ptr() for y in ys]),
@@ -119,6 +131,17 @@ def decode_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequen
     """``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]`` from ``T*L`` raw head tensors (task-major); ``smax_t`` has a last
     dimension of 0 when the shapes rule the score summary out."""
     return _decode_impl(levels, nc, strides)
+
+
+@torch.library.custom_op("cerb::decode_out", mutates_args=("out",))
+def decode_out_op(levels: Sequence[torch.Tensor], nc: Sequence[int], strides: Sequence[float], out: Sequence[torch.Tensor]) -> None:
+    """``cerb::decode`` writing into caller-provided buffers ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``."""
+    _decode_impl(levels, nc, strides, out=out)
+
+
+@decode_out_op.register_fake
+def _(levels, nc, strides, out):
+    return None
 
 
 @torch.library.custom_op("cerb::decode_split", mutates_args=())
@@ -161,6 +184,7 @@ def _nms_impl(
     max_wh: float,
     smax: Sequence[torch.Tensor],
     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    stats: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     T = len(preds)
@@ -195,14 +219,16 @@ def _nms_impl(
         ok = ok and all(p.data_ptr() == q.data_ptr() for p, q in zip(preds, ps))  # no hidden copies
         if ok:
             sm_arr = _lib.ptr_array([s.data_ptr() for s in smax])
+    if stats is not None and (stats.dtype != torch.int64 or tuple(stats.shape) != (T, B, 2) or stats.device != dev or not stats.is_contiguous()):
+        raise ValueError("stats must be a contiguous int64 [T, B, 2] tensor on the input device")
     with torch.cuda.device(dev):
-        rc = lib.cerb_nms(
+        rc = lib.cerb_nms_stats(
             _lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
             float(conf_thres), float(iou_thres), cls_arr, len(classes) if classes is not None else 0,
             int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh),
             sm_arr,
             dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
-            _stream_ptr(dev),
+            stats.data_ptr() if stats is not None else None, _stream_ptr(dev),
         )
     _lib.check(rc)
     return dets, counts
@@ -312,13 +338,29 @@ def find_summary(y: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------- friendly wrappers
-def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float]) -> List[torch.Tensor]:
+def decode_buffers(task_levels: Sequence[Sequence[torch.Tensor]]) -> List[torch.Tensor]:
+    """Static output buffers for ``decode_heads(..., out=...)``: ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``."""
+    first = task_levels[0][0]
+    B = int(first.shape[0])
+    sizes = [int(x.shape[2]) * int(x.shape[3]) for x in task_levels[0]]
+    A, R = sum(sizes), _summary_len(sizes, first.element_size())
+    ncs = [int(lv[0].shape[1]) - 64 for lv in task_levels]
+    return ([torch.empty((B, 4 + n, A), dtype=first.dtype, device=first.device) for n in ncs]
+            + [torch.empty((B, n, R), dtype=first.dtype, device=first.device) for n in ncs])
+
+
+def decode_heads(task_levels: Sequence[Sequence[torch.Tensor]], strides: Sequence[float],
+                 out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """``task_levels[t][l]`` = raw head tensor ``[B, 64+nc_t, H_l, W_l]`` -> ``y_t [B, 4+nc_t, A]``
     for every task in one launch (reference Detect.forward eval branch, models/yolo.py:93-99).
-    The kernel also leaves a score summary per task, remembered for ``nms_batched``."""
+    The kernel also leaves a score summary per task, remembered for ``nms_batched``.
+    ``out=decode_buffers(task_levels)`` writes into caller-owned static buffers."""
     flat = [x for lv in task_levels for x in lv]
     nc = [int(lv[0].shape[1]) - 64 for lv in task_levels]
-    out = decode_op(flat, nc, [float(s) for s in strides])
+    if out is not None:
+        decode_out_op(flat, nc, [float(s) for s in strides], list(out))
+    else:
+        out = decode_op(flat, nc, [float(s) for s in strides])
     T = len(nc)
     ys, sms = out[:T], out[T:]
     for y, sm in zip(ys, sms):
@@ -377,6 +419,22 @@ def nms_batched(
     return nms_op(*args)
 
 
+def nms_statistics(preds: Sequence[torch.Tensor], **kw) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``nms_batched`` plus per-segment counters: returns ``(dets, counts, stats[T, B, 2])`` with the IoU tests made and
+    the candidates consumed per (task, image) segment (``cerb_nms_stats``; bench.py's IoU pairs/s)."""
+    preds = list(preds)
+    T, B = len(preds), int(preds[0].shape[0])
+    stats = torch.zeros((T, B, 2), dtype=torch.int64, device=preds[0].device)
+    use_summary = kw.pop("use_summary", True)
+    found = [find_summary(p) for p in preds] if use_summary else []
+    smax = found if found and all(f is not None for f in found) else []
+    dets, counts = _nms_impl(preds, float(kw.get("conf_thres", 0.25)), float(kw.get("iou_thres", 0.45)),
+                             None if kw.get("classes") is None else [int(c) for c in kw["classes"]], bool(kw.get("agnostic", False)),
+                             bool(kw.get("multi_label", False)), int(kw.get("max_det", 300)), int(kw.get("max_nms", MAX_NMS)),
+                             float(kw.get("max_wh", MAX_WH)), smax, None, stats)
+    return dets, counts, stats
+
+
 def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Sequence[int], iou_thres: float,
                      scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Batched GPU form of the reference's per-image tail after NMS (cerberusdet_inference.py:140-155):
@@ -386,9 +444,9 @@ def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Se
     lib = _lib.load()
     _require_cuda(dets, "dets")
     T, B, max_det, _ = dets.shape
-    if T * max_det > 1024:
-        raise ValueError("cross_task_merge supports T*max_det <= 1024 rows per image")
     dets, counts = dets.contiguous(), counts.contiguous()
+    ws_bytes = int(lib.cerb_cross_task_workspace_bytes(T, B, max_det))  # 0 while T*max_det <= 1024
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dets.device) if ws_bytes else None
     out = torch.empty((B, T * max_det, 6), dtype=torch.float32, device=dets.device)
     out_counts = torch.empty((B,), dtype=torch.int32, device=dets.device)
     if scale is not None:
@@ -396,9 +454,10 @@ def cross_task_merge(dets: torch.Tensor, counts: torch.Tensor, class_offsets: Se
         if tuple(scale.shape) != (B, 5):
             raise ValueError("scale must be [B, 5]")
     with torch.cuda.device(dets.device):
-        rc = lib.cerb_cross_task(dets.data_ptr(), counts.data_ptr(), T, B, max_det, _lib.int_array([int(o) for o in class_offsets]),
-                                 float(iou_thres), scale.data_ptr() if scale is not None else None, out.data_ptr(),
-                                 out_counts.data_ptr(), _stream_ptr(dets.device))
+        rc = lib.cerb_cross_task_ws(dets.data_ptr(), counts.data_ptr(), T, B, max_det, _lib.int_array([int(o) for o in class_offsets]),
+                                    float(iou_thres), scale.data_ptr() if scale is not None else None, out.data_ptr(),
+                                    out_counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
+                                    _stream_ptr(dets.device))
     _lib.check(rc)
     return out, out_counts
 

@@ -112,7 +112,7 @@ def install(import_all: bool = False, train: bool = False, val: bool = False) ->
                            and anchor_points.dtype == pred_dist.dtype)
                 if on_path and torch.is_autocast_enabled():
                     # autocast: fp32 softmax -> fp16 probabilities -> fp16 matmul (fp32 accumulate): the kernels' half path
-                    on_path = pred_dist.dtype == torch.float16 and torch.get_autocast_gpu_dtype() == torch.float16
+                    on_path = pred_dist.dtype == torch.float16 and torch.get_autocast_dtype("cuda") == torch.float16
                 elif on_path:
                     on_path = pred_dist.dtype in (torch.float16, torch.float32)
                 if not on_path:  # CPU tensors, reg_max != 16, mixed dtypes: the reference's own code

@@ -110,3 +110,134 @@ class DetectionGatherer:
         c = self.all[:, self._n_d :].view(torch.int32).view(self.world, self.T, self.b_loc)
         return (d.permute(1, 0, 2, 3, 4).reshape(self.T, self.world * self.b_loc, self.max_det, 6),
                 c.permute(1, 0, 2).reshape(self.T, self.world * self.b_loc))
+
+
+# ------------------------------------------------------------------------------------------------ per-batch delivery to rank 0
+class GatherDelivery:
+    """Per-batch delivery of the padded detections to ``dst`` by one asynchronous ``dist.gather`` per batch
+    (``DetectionGatherer``), two alternating buffers.  Works on every backend (NCCL on GPUs, gloo in the CPU tests)."""
+
+    kind = "one asynchronous gather per batch (torch.distributed)"
+
+    def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
+        self.g = [DetectionGatherer(T, b_loc, max_det, device, dst=dst, group=group) for _ in range(2)]
+        self.outs = [g.out for g in self.g]
+
+    def before_write(self, slot: int) -> None:
+        """Call before a kernel overwrites ``outs[slot]``: the previous batch in that slot must have left."""
+        self.g[slot].wait()
+
+    def after_write(self, slot: int) -> None:
+        """Call after the kernel that filled ``outs[slot]`` was enqueued: starts the delivery of that batch."""
+        self.g[slot].launch()
+
+    def drain(self) -> None:
+        for g in self.g:
+            g.wait()
+
+    def result(self, slot: int):
+        return self.g[slot].result()
+
+
+class PeerDelivery:
+    """Per-batch delivery WITHOUT a collective on the data path: every rank's NMS kernel writes its padded detections
+    straight into rank ``dst``'s memory over NVLink -- ``outs[slot]`` on rank r are views of rank dst's symmetric-memory
+    buffer (``torch.distributed._symmetric_memory``: peer-mapped device memory), region (slot, r).  What remains per batch
+    is one flag per rank: the writer signals "slot filled" after its kernel, ``dst`` acknowledges once it has seen every
+    rank's flag, and a writer waits for that acknowledgement before it reuses the slot (two batches later, so in steady
+    state it never blocks).  No NCCL kernel takes SMs from the next batch's decode, no stream waits for a gather.
+
+    The NMS kernel only ever writes ``dets`` / ``counts`` (24-byte rows, the zero fill of unused rows, one count per
+    segment); remote stores are posted, and their visibility to ``dst`` is ordered by the kernel boundary before the
+    flag (stream order on the writer, acquire on the reader's wait)."""
+
+    kind = "NMS kernel stores straight into rank 0's peer-mapped symmetric memory over NVLink + one flag per rank and batch"
+
+    def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), dst
+        self.T, self.b_loc, self.max_det = T, b_loc, max_det
+        self.n_d, self.n_c = T * b_loc * max_det * 6, T * b_loc
+        self.n = (self.n_d + self.n_c + 63) // 64 * 64  # words per (slot, rank) region, 256-byte aligned
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass  # newer builds enable it inside rendezvous()
+        self.local = symm_mem.empty(2 * self.world * self.n, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.local, group)
+        self.outs = []
+        for slot in range(2):
+            off = (slot * self.world + self.rank) * self.n
+            if self.rank == dst:
+                region = self.local[off : off + self.n]
+            else:
+                region = self.hdl.get_buffer(dst, (self.n,), torch.float32, off)  # rank dst's memory, mapped here
+            self.outs.append((region[: self.n_d].view(T, b_loc, max_det, 6),
+                              region[self.n_d : self.n_d + self.n_c].view(torch.int32).view(T, b_loc)))
+        self.side = torch.cuda.Stream(device=device)
+        self.used = [False, False]
+        self.hdl.barrier(channel=7)
+
+    def before_write(self, slot: int) -> None:
+        if self.rank != self.dst and self.used[slot]:
+            self.hdl.wait_signal(self.dst, channel=2 + slot)  # dst has taken the batch that was in this slot
+
+    def after_write(self, slot: int) -> None:
+        self.used[slot] = True
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)  # the flag follows the kernel that filled the slot; the compute stream runs on
+        with torch.cuda.stream(self.side):
+            if self.rank != self.dst:
+                self.hdl.put_signal(self.dst, channel=slot)
+            else:
+                for r in range(self.world):
+                    if r != self.dst:
+                        self.hdl.wait_signal(r, channel=slot)      # rank r's batch has arrived
+                for r in range(self.world):
+                    if r != self.dst:
+                        self.hdl.put_signal(r, channel=2 + slot)   # ... and may be overwritten two batches from now
+
+    def drain(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.side)
+        if self.rank != self.dst:  # consume outstanding acknowledgements so that the next run starts clean
+            for slot in range(2):
+                if self.used[slot]:
+                    self.hdl.wait_signal(self.dst, channel=2 + slot)
+                    self.used[slot] = False
+        else:
+            self.used = [False, False]
+
+    def result(self, slot: int):
+        """``(dets[T, world*B_loc, max_det, 6], counts[T, world*B_loc])`` on ``dst`` (after ``drain()`` and a device
+        synchronisation), ``(None, None)`` elsewhere."""
+        if self.rank != self.dst:
+            return None, None
+        reg = self.local[slot * self.world * self.n : (slot + 1) * self.world * self.n].view(self.world, self.n)
+        d = reg[:, : self.n_d].reshape(self.world, self.T, self.b_loc, self.max_det, 6)
+        c = reg[:, self.n_d : self.n_d + self.n_c].contiguous().view(torch.int32).view(self.world, self.T, self.b_loc)
+        return (d.permute(1, 0, 2, 3, 4).reshape(self.T, self.world * self.b_loc, self.max_det, 6),
+                c.permute(1, 0, 2).reshape(self.T, self.world * self.b_loc))
+
+
+def make_delivery(T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None, prefer_peer: bool = True):
+    """The per-batch delivery to rank ``dst``: peer-mapped symmetric memory on CUDA when every rank can set it up
+    (all ranks agree, so nobody is left in a collective alone), else the gather."""
+    import os
+
+    want_peer = prefer_peer and torch.device(device).type == "cuda" and os.environ.get("CERB_DELIVERY", "peer") != "gather"
+    if want_peer:
+        ok, deliv = 1, None
+        try:
+            deliv = PeerDelivery(T, b_loc, max_det, device, dst=dst, group=group)
+        except Exception as exc:  # pragma: no cover - depends on the box / torch build
+            import sys
+
+            print(f"[cerberusdet_b200.shard] symmetric memory unavailable ({type(exc).__name__}: {exc}); using the gather", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 1:
+            return deliv
+    return GatherDelivery(T, b_loc, max_det, device, dst=dst, group=group)

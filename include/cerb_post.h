@@ -116,6 +116,16 @@ int cerb_nms(const void* const* pred, const int* nc, int T, int B, int A, int dt
              size_t workspace_bytes, void* stream);
 
 /*
+ * cerb_nms with per-segment statistics: stats is a device array [T*B][2] of 64-bit counters that receives, per
+ * (task, image) segment, the number of IoU tests made and the number of candidates consumed from the sorted order
+ * (bench.py reports IoU pairs/s from it).  stats == NULL is exactly cerb_nms.
+ */
+int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+                   double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
+                   int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace,
+                   size_t workspace_bytes, unsigned long long* stats, void* stream);
+
+/*
  * Decode + NMS for T task heads in one call (two launches on `stream`, no host work in between): the raw head
  * tensors go in, the padded detections come out; `y` (and `smax`, may be NULL) are caller-provided buffers that
  * receive the decoded predictions / score summary on the way (they are what Detect.forward would have returned).
@@ -140,10 +150,17 @@ int cerb_decode_nms(const void* const* lvl, const int* nc, int T, int L, int B, 
  *   scale          optional device [B, 5] = (gain, pad_x, pad_y, orig_w, orig_h) per image, or NULL
  *   out            [B, T*max_det, 6] merged rows (x1, y1, x2, y2, conf, global cls), task order kept;
  *   out_counts     [B]
- * Needs T*max_det <= 1024 (the per-image IoU bitmask lives in shared memory).
+ * cerb_cross_task needs T*max_det <= 1024 (the per-image tables then always fit shared memory); cerb_cross_task_ws lifts
+ * that (the reference's detect.py:124 runs max_det = 1000): images whose rows (the sum of the tasks' counts) exceed 1024
+ * keep their tables in `workspace` (device memory, cerb_cross_task_workspace_bytes(T, B, max_det) bytes, 0 when
+ * T*max_det <= 1024), every other image still runs out of shared memory.  max_det <= 65535.
  */
 int cerb_cross_task(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
                     double iou_thres, const float* scale, float* out, int* out_counts, void* stream);
+size_t cerb_cross_task_workspace_bytes(int T, int B, int max_det);
+int cerb_cross_task_ws(const float* dets, const int* counts, int T, int B, int max_det, const int* class_offset,
+                       double iou_thres, const float* scale, float* out, int* out_counts, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /*
  * Which detections are correct at each IoU threshold, for a whole batch of ONE task in one launch (one CTA per image).

@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from cerberusdet_b200 import ops  # noqa: E402
-from cerberusdet_b200.shard import DetectionGatherer, gather_detections, shard_range  # noqa: E402
+from cerberusdet_b200.pipeline import PostHeadPipeline  # noqa: E402
+from cerberusdet_b200.shard import DetectionGatherer, GatherDelivery, PeerDelivery, gather_detections, make_delivery, shard_range  # noqa: E402
 from cerberusdet_b200.synth import STRIDES, synth_heads  # noqa: E402
 
 
@@ -41,8 +42,37 @@ def main():
     mine2 = shard_range(n2, rank, world)
     d2l, c2l = run(mine2)
     d2, c2 = gather_detections(d2l, c2l, dst=0, n_images=n2)
+    # (c) the streaming engine with both per-batch deliveries: the NMS kernel writes straight into rank 0's peer-mapped
+    # symmetric memory (no collective on the data path) / one asynchronous gather per batch; several batches per slot
+    dev_heads = [[x.to(dev) for x in lv] for lv in heads]
+    kinds = []
+    streamed = {}
+    for prefer_peer in (True, False):
+        deliv = make_delivery(len(ncs), len(mine), kw["max_det"], dev, prefer_peer=prefer_peer)
+        kinds.append(type(deliv).__name__)
+        pipe = PostHeadPipeline(dev_heads, STRIDES, kw, outs=deliv.outs)
+        for rep in range(2):  # run the stream twice: the flags / buffers must be reusable
+            pipe.k, pipe.pending = 0, None
+            n_steps = 5
+            for k in range(n_steps):
+                deliv.before_write((k - 1) & 1)
+                done = pipe.step()
+                if done is not None:
+                    deliv.after_write(done)
+            deliv.before_write((n_steps - 1) & 1)
+            last = pipe.flush()
+            deliv.after_write(last)
+            deliv.drain()
+            dist.barrier()
+            torch.cuda.synchronize()
+            got = deliv.result(last)
+            streamed[(kinds[-1], rep)] = got
+        del pipe, deliv
     if rank == 0:
         full_d, full_c = run(range(n_images))
+        for key, (sd, sc) in streamed.items():
+            assert torch.equal(sc, full_c) and torch.equal(sd, full_d), f"streamed delivery {key}: rank 0's buffer != single-GPU result"
+        print("DELIVERIES", kinds)
         assert torch.equal(c, full_c) and torch.equal(d, full_d), "equal shards: gathered != single-GPU result"
         full_d2, full_c2 = run(range(n2))
         assert torch.equal(c2, full_c2) and torch.equal(d2, full_d2), "ragged shards: gathered != single-GPU result"

@@ -196,6 +196,38 @@ def test_cross_task_merge_matches_host_tail(clustered, ties, thr, with_scale):
         assert torch.equal(got, want), b
 
 
+@pytest.mark.parametrize("thr", [0.8, 0.3])
+def test_cross_task_merge_beyond_1024_rows(thr):
+    """max_det = 1000 (the reference's detect.py:124): T*max_det = 3000 rows per image.  Images whose rows exceed the
+    shared-memory tables run out of the global workspace, the others out of shared memory -- same bits as the host tail."""
+    from cerberusdet_b200 import cross_task as ct
+    from cerberusdet_b200.ops import cross_task_merge
+
+    gen = torch.Generator().manual_seed(11)
+    T, B, md = 3, 3, 1000
+    dets, counts = _random_task_dets(gen, T, B, md, clustered=False, ties=False)
+    counts[:, 0] = torch.tensor([900, 700, 1000], dtype=torch.int32)   # 2600 rows: workspace path
+    counts[:, 2] = torch.tensor([300, 0, 250], dtype=torch.int32)      # 550 rows: shared-memory path
+    for b in (0, 2):
+        for t in range(T):
+            n = int(counts[t, b])
+            c = torch.rand(n, 2, generator=gen) * 500 + 50
+            wh = 30 + torch.rand(n, 2, generator=gen) * 60
+            sc = torch.rand(n, generator=gen).sort(descending=True).values
+            dets[t, b] = 0
+            dets[t, b, :n] = torch.cat((c - wh / 2, c + wh / 2, sc[:, None], torch.randint(0, 12, (n, 1), generator=gen).float()), 1)
+    names = {"a": ["x"] * 12, "b": ["y"] * 12, "c": ["z"] * 12}
+    maps, _ = ct.category_maps(names)
+    merged, mc = cross_task_merge(dets.cuda(), counts.cuda(), [0, 12, 24], thr)
+    merged, mc = merged.cpu(), mc.cpu()
+    for b in range(B):
+        per_task = {t: dets[k, b, : int(counts[k, b])] for k, t in enumerate(names)}
+        want = ct.suppress_between_tasks(ct.combine_tasks(per_task, maps), maps, thr)
+        got = merged[b, : int(mc[b])]
+        assert got.shape == want.shape, (b, got.shape, want.shape)
+        assert torch.equal(got, want), b
+
+
 def test_cross_task_merge_everything_deleted_keeps_everything():
     """Two tasks with one identical box each and equal scores: the column wins the tie and the row is deleted;
     with mutual total deletion the reference returns the input unchanged (general.py:551-552)."""

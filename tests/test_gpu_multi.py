@@ -18,3 +18,4 @@ def test_sharded_equals_single_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MULTI_GPU_OK" in out.stdout
+    assert "GatherDelivery" in out.stdout  # (PeerDelivery too wherever symmetric memory is available: printed, not required)

@@ -39,8 +39,14 @@ def test_argument_validation_without_gpu():
     rc = lib.cerb_nms(_lib.ptr_array([0]), _lib.int_array([5]), 1, 1, 10, 7, 0.25, 0.45, None, 0, 0, 0, 300, 30000,
                       7680.0, None, None, None, None, 0, None)
     assert rc == _lib.CERB_EINVAL and b"dtype" in lib.cerb_last_error()
-    rc = lib.cerb_cross_task(None, None, 3, 2, 400, _lib.int_array([0, 20, 39]), 0.8, None, None, None, None)
-    assert rc == _lib.CERB_EINVAL and b"1024" in lib.cerb_last_error()
+    # more than 1024 rows per image need the workspace form (nothing is dereferenced before the check fails)
+    fake = ctypes.c_void_p(256)
+    rc = lib.cerb_cross_task(fake, fake, 3, 2, 400, _lib.int_array([0, 20, 39]), 0.8, None, fake, fake, None)
+    assert rc == _lib.CERB_ENOSPC and b"workspace" in lib.cerb_last_error()
+    assert lib.cerb_cross_task_workspace_bytes(3, 2, 300) == 0 and lib.cerb_cross_task_workspace_bytes(3, 2, 400) > 2 * 1200 * 38 * 4
+    # thread-local test knobs: unknown names are refused, known ones set and reset
+    assert lib.cerb_debug_set(b"no_such_knob", 1) == _lib.CERB_EINVAL and b"unknown knob" in lib.cerb_last_error()
+    assert lib.cerb_debug_set(b"nms_minb", 1) == 0 and lib.cerb_debug_reset() == 0
     rc = lib.cerb_nms(_lib.ptr_array([0]), _lib.int_array([5]), 1, 1, 10, 0, 1.5, 0.45, None, 0, 0, 0, 300, 30000,
                       7680.0, None, None, None, None, 0, None)
     assert rc == _lib.CERB_EINVAL and lib.cerb_last_error().startswith(b"Invalid Confidence threshold")
@@ -90,7 +96,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's own code when its tree is there (/root/reference here, oracle/_ref on the GPU box), else the port
+    assert line["cpu_baseline"]["kind"] == ("reference" if REF else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("BASELINE config 3")
 
@@ -295,7 +302,22 @@ for rep in range(3):                                   # buffers are reused acro
         assert torch.equal(D, full_d + rep) and torch.equal(C, full_c)
     else:
         assert D is None and C is None
+# the per-batch delivery interface the streaming engine drives (CPU: always the gather flavour), several batches per slot
+from cerberusdet_b200.shard import make_delivery, GatherDelivery
+deliv = make_delivery(T, BL, MD, "cpu", dst=0)
+assert isinstance(deliv, GatherDelivery) and len(deliv.outs) == 2
+for step in range(5):
+    slot = step & 1
+    deliv.before_write(slot)
+    d, c = deliv.outs[slot]
+    d.copy_(full_d[:, rank * BL:(rank + 1) * BL] * (step + 1)); c.copy_(full_c[:, rank * BL:(rank + 1) * BL])
+    deliv.after_write(slot)
+deliv.drain()
+D, C = deliv.result(0)  # slot 0 holds step 4
 if rank == 0:
+    assert torch.equal(D, full_d * 5) and torch.equal(C, full_c)
+    D1, _ = deliv.result(1)
+    assert torch.equal(D1, full_d * 4)
     print("GATHERER_OK")
 dist.destroy_process_group()
 """
