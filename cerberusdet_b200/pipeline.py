@@ -4,7 +4,7 @@ in which the decode of batch k overlaps the NMS of batch k-1.
 Why overlap.  The decode kernel is memory-bound (all SMs streaming 330 MB per config-3 batch); the NMS kernel is a
 latency-bound chain of short phases that keeps the SMs ~30 % busy and touches little memory.  Run back to back they
 take 64 + 52 us; run concurrently -- NMS of the previous batch on a second stream while the next batch is decoded --
-a step takes ~98 us (profiles/r02_pipeline.md).  Both kernels are the same launches as in the serial path; only their
+a step takes ~98 us (profiles/r02_nms.md, "The overlapped step").  Both kernels are the same launches as in the serial path; only their
 placement in time changes, so results are bit-identical to ``ops.decode_heads`` + ``ops.nms_batched``.
 
 Step k (one CUDA-graph replay):      stream A:  decode(inputs)      -> Y[k & 1]
