@@ -19,6 +19,7 @@ EXPORTS = (
     "cerb_last_error",
     "cerb_decode",
     "cerb_decode_split",
+    "cerb_head_tail",
     "cerb_summary_row_len",
     "cerb_nms_workspace_bytes",
     "cerb_nms",
@@ -64,6 +65,9 @@ def load() -> ctypes.CDLL:
     lib.cerb_decode.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
     lib.cerb_decode_split.restype = i
     lib.cerb_decode_split.argtypes = [vpp, vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
+    if hasattr(lib, "cerb_head_tail") or "CERB_LIB" not in os.environ:
+        lib.cerb_head_tail.restype = i
+        lib.cerb_head_tail.argtypes = [vpp] * 6 + [ip, ip, ip, i, i, i, ip, ip, fp, i, vpp, vpp, ip, vp]
     lib.cerb_summary_row_len.restype = sz
     lib.cerb_summary_row_len.argtypes = [i, i]
     lib.cerb_nms_workspace_bytes.restype = sz

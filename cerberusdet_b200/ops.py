@@ -385,6 +385,104 @@ def decode_heads_split(task_box_levels: Sequence[Sequence[torch.Tensor]], task_c
     return ys
 
 
+def _head_tail_impl(box_feats: Sequence[torch.Tensor], cls_feats: Sequence[torch.Tensor], box_w: Sequence[torch.Tensor],
+                    box_b: Sequence[torch.Tensor], cls_w: Sequence[torch.Tensor], cls_b: Sequence[torch.Tensor],
+                    strides: Sequence[float], T: int) -> List[torch.Tensor]:
+    """``cerb_head_tail`` on flat task-major lists of T*L tensors.  Returns ``[y_0 .. y_{T-1}, smax_0 .. smax_{T-1}]``."""
+    lib = _lib.load()
+    n = len(box_feats)
+    if T <= 0 or n % T or any(len(z) != n for z in (cls_feats, box_w, box_b, cls_w, cls_b)):
+        raise ValueError("head_tail: every list must hold T*L tensors, task-major")
+    L = n // T
+    if len(strides) != L:
+        raise ValueError(f"expected {L} strides, got {len(strides)}")
+    first = box_feats[0]
+    _require_cuda(first, "head-tail inputs")
+    if first.dtype != torch.float16:
+        raise TypeError("head_tail runs on float16 tensors only (tcgen05 kind::f16); use the convolutions + decode_heads_split for float32")
+    B = int(first.shape[0])
+    H = [int(box_feats[l].shape[2]) for l in range(L)]
+    W = [int(box_feats[l].shape[3]) for l in range(L)]
+    A = sum(h * w for h, w in zip(H, W))
+    c2 = [int(box_feats[t * L].shape[1]) for t in range(T)]
+    c3 = [int(cls_feats[t * L].shape[1]) for t in range(T)]
+    nc = [int(cls_w[t * L].shape[0]) for t in range(T)]
+    keep = []  # dense copies (non-contiguous / misaligned inputs only) must outlive the launch
+
+    def dense(x, shape, what, t, l):
+        if x.device != first.device or x.dtype != first.dtype:
+            raise TypeError("all head-tail tensors must share device and dtype")
+        if tuple(x.shape) != shape and not (x.dim() == 4 and tuple(x.shape) == shape + (1, 1)):
+            raise ValueError(f"task {t} level {l}: {what} expected {shape}, got {tuple(x.shape)}")
+        d = _dense16(x.reshape(shape))
+        if d.data_ptr() != x.data_ptr():
+            keep.append(d)
+        return d.data_ptr()
+
+    ptrs = [[] for _ in range(6)]
+    for t in range(T):
+        for l in range(L):
+            i = t * L + l
+            ptrs[0].append(dense(box_feats[i], (B, c2[t], H[l], W[l]), "box features", t, l))
+            ptrs[1].append(dense(cls_feats[i], (B, c3[t], H[l], W[l]), "class features", t, l))
+            ptrs[2].append(dense(box_w[i], (64, c2[t]), "box weight", t, l))
+            ptrs[3].append(dense(box_b[i], (64,), "box bias", t, l))
+            ptrs[4].append(dense(cls_w[i], (nc[t], c3[t]), "class weight", t, l))
+            ptrs[5].append(dense(cls_b[i], (nc[t],), "class bias", t, l))
+    R = _summary_len([h * w for h, w in zip(H, W)], 2)
+    ys = [torch.empty((B, 4 + nc[t], A), dtype=first.dtype, device=first.device) for t in range(T)]
+    sm = [torch.empty((B, nc[t], R), dtype=first.dtype, device=first.device) for t in range(T)]
+    written = ctypes.c_int(0)
+    with torch.cuda.device(first.device):
+        rc = lib.cerb_head_tail(*[_lib.ptr_array(p) for p in ptrs], _lib.int_array(c2), _lib.int_array(c3), _lib.int_array(nc),
+                                T, L, B, _lib.int_array(H), _lib.int_array(W), _lib.float_array([float(s) for s in strides]),
+                                _lib.CERB_F16, _lib.ptr_array([y.data_ptr() for y in ys]),
+                                _lib.ptr_array([x.data_ptr() for x in sm]) if R else None, ctypes.byref(written),
+                                _stream_ptr(first.device))
+    _lib.check(rc)
+    for x in keep:  # the kernel is only enqueued: keep temporaries alive on this stream
+        x.record_stream(torch.cuda.current_stream(first.device))
+    return ys + sm
+
+
+@torch.library.custom_op("cerb::head_tail", mutates_args=())
+def head_tail_op(box_feats: Sequence[torch.Tensor], cls_feats: Sequence[torch.Tensor], box_w: Sequence[torch.Tensor],
+                 box_b: Sequence[torch.Tensor], cls_w: Sequence[torch.Tensor], cls_b: Sequence[torch.Tensor],
+                 strides: Sequence[float], T: int) -> List[torch.Tensor]:
+    return _head_tail_impl(box_feats, cls_feats, box_w, box_b, cls_w, cls_b, strides, T)
+
+
+@head_tail_op.register_fake
+def _(box_feats, cls_feats, box_w, box_b, cls_w, cls_b, strides, T):
+    L = len(box_feats) // T
+    first = box_feats[0]
+    sizes = [int(box_feats[l].shape[2]) * int(box_feats[l].shape[3]) for l in range(L)]
+    A, R = sum(sizes), _summary_len(sizes, 2)
+    ncs = [int(cls_w[t * L].shape[0]) for t in range(T)]
+    return ([first.new_empty((first.shape[0], 4 + n, A)) for n in ncs] + [first.new_empty((first.shape[0], n, R)) for n in ncs])
+
+
+def head_tail(task_box_feats: Sequence[Sequence[torch.Tensor]], task_cls_feats: Sequence[Sequence[torch.Tensor]],
+              task_box_w: Sequence[Sequence[torch.Tensor]], task_box_b: Sequence[Sequence[torch.Tensor]],
+              task_cls_w: Sequence[Sequence[torch.Tensor]], task_cls_b: Sequence[Sequence[torch.Tensor]],
+              strides: Sequence[float]) -> List[torch.Tensor]:
+    """Head-tail fusion: the last 1x1 convolutions of both towers of every (task, level)
+    (``cv2[l][-1]``: c2 -> 64, ``cv3[l][-1]``: c3 -> nc; reference models/yolo.py:81-84,89-90) + concat + eval decode
+    (yolo.py:93-99) in one tcgen05 kernel.  ``task_box_feats[t][l]`` ``[B, c2, H_l, W_l]`` / ``task_cls_feats[t][l]``
+    ``[B, c3, H_l, W_l]`` are the inputs of those convolutions, the weights ``[64, c2(,1,1)]`` / ``[nc, c3(,1,1)]`` and
+    biases their parameters.  float16 only.  Returns ``y_t [B, 4+nc_t, A]`` per task (score summaries remembered for
+    ``nms_batched`` like ``decode_heads`` does)."""
+    flat = lambda z: [x for lv in z for x in lv]  # noqa: E731
+    T = len(task_box_feats)
+    out = head_tail_op(flat(task_box_feats), flat(task_cls_feats), flat(task_box_w), flat(task_box_b), flat(task_cls_w),
+                       flat(task_cls_b), [float(s) for s in strides], T)
+    ys, sms = out[:T], out[T:]
+    for y, sm in zip(ys, sms):
+        if sm.shape[-1]:
+            _remember_summary(y, sm)
+    return ys
+
+
 def nms_batched(
     preds: Sequence[torch.Tensor],
     conf_thres: float = 0.25,

@@ -75,6 +75,26 @@ int cerb_decode_split(const void* const* box_lvl, const void* const* cls_lvl, co
                       int* summary_written, void* stream);
 
 /*
+ * Head-tail fusion (fp16 only): the LAST 1x1 convolution of both conv towers of every (task, level)
+ *   box = cv2[l][-1](u2), cls = cv3[l][-1](u3)   (cerberusdet/models/yolo.py:81-84, applied at :89-90)
+ * fused with the channel concat (:90) and the eval decode (:93-99) in one persistent tcgen05 kernel: the raw head
+ * tensor [B, 64+nc, H, W] is neither written nor re-read.  Per 128-anchor tile the two GEMMs
+ * [128 x c2] x [c2 x 64] and [128 x c3] x [c3 x nc] run on the tensor cores (fp32 accumulators in TMEM, operands
+ * brought in by TMA), and every epilogue thread decodes the anchor whose logits it reads back.
+ *
+ *   box_feat[t*L + l]  [B, c2[t], H[l], W[l]]  input of cv2[l][-1]      cls_feat[t*L + l]  [B, c3[t], H[l], W[l]]
+ *   box_w[t*L + l]     [64, c2[t]] (the 1x1 kernel squeezed), box_b [64]; cls_w [nc[t], c3[t]], cls_b [nc[t]]
+ *   y, smax, summary_written as in cerb_decode.
+ * Needs c2, c3 multiples of 16, every H[l]*W[l] a multiple of 8 (16-byte rows for TMA), nc <= 192, 16-byte aligned
+ * tensors; otherwise CERB_EINVAL (run the convolutions and cerb_decode_split instead).  The convolution output is
+ * rounded to half (fp32 accumulation + bias, one rounding) before the decode, like the reference's half conv.
+ */
+int cerb_head_tail(const void* const* box_feat, const void* const* cls_feat, const void* const* box_w,
+                   const void* const* box_b, const void* const* cls_w, const void* const* cls_b, const int* c2,
+                   const int* c3, const int* nc, int T, int L, int B, const int* H, const int* W, const float* strides,
+                   int dtype, void* const* y, void* const* smax, int* summary_written, void* stream);
+
+/*
  * Score summary (optional by-product of cerb_decode, optional input of cerb_nms).
  *   smax[t]   [B, nc[t], R] in the tensor dtype, R = cerb_summary_row_len(A, dtype): entry (b, c, i) is
  *             the maximum of the 16-byte score vector i of class c, i.e. of the scores of anchors
