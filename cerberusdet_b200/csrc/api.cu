@@ -24,13 +24,16 @@ enum Knob {
     K_CHUNK_CAP,      // lazy top-k: chunk capacity (16..4096)
     K_CHUNK_FIRST,    // lazy top-k: first chunk target
     K_HIST_SAMPLE,    // stride of the estimating histogram
+    K_HT_ORDER,       // head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = one contiguous run of tiles per CTA
+    K_HT_STAGES,      // head-tail kernel: cap on the activation ring depth (2..8)
     K_COUNT
 };
 static const char* const kKnobName[K_COUNT] = {"decode_pipe", "decode_order", "decode_vec", "decode_l2hint", "nms_minb",
-                                               "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample"};
+                                               "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample",  "ht_order",
+                                               "ht_stages"};
 static const char* const kKnobEnv[K_COUNT] = {"CERB_DEBUG_DECODE_PIPE", "CERB_DEBUG_DECODE_ORDER", "CERB_DEBUG_DECODE_VEC",
                                               "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL",
-                                              nullptr, nullptr, nullptr};
+                                              nullptr, nullptr, nullptr, "CERB_DEBUG_HT_ORDER", "CERB_DEBUG_HT_STAGES"};
 struct KnobTable {
     int v[K_COUNT];
     bool set[K_COUNT];
@@ -51,6 +54,13 @@ static bool knob(Knob k, int* out) {
     if (g_knobs.set[k]) { *out = g_knobs.v[k]; return true; }
     const KnobTable& e = env_knobs();
     if (e.set[k]) { *out = e.v[k]; return true; }
+    return false;
+}
+
+// knob lookup by name for the other translation units (head_tail.cu)
+bool cerb_debug_knob(const char* name, int* out) {
+    for (int i = 0; i < K_COUNT; ++i)
+        if (strcmp(name, kKnobName[i]) == 0) return knob((Knob)i, out);
     return false;
 }
 

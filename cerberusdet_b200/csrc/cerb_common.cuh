@@ -235,3 +235,4 @@ __device__ __forceinline__ void stg_stream16(void* p, uint4 v) {
 
 // host-side error plumbing (api.cu)
 void cerb_set_error(const char* fmt, ...);
+bool cerb_debug_knob(const char* name, int* out);  // thread-local / environment test knob, false when unset

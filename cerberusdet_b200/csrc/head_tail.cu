@@ -58,6 +58,8 @@ struct HeadTailParams {
     int off_w2, off_w3, off_bias, off_bar;  // byte offsets inside the (1024-aligned) dynamic shared memory
     int tmem_cols, buf_cols;
     int srow;                               // score-summary row length (cerb_summary_row_len)
+    int chunked;                            // 1: CTA i owns one contiguous run of tiles (few (task, level) changes, so few
+                                            // weight reloads); 0: tiles dealt round-robin
 };
 
 // ---- PTX wrappers
@@ -176,14 +178,27 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
     __syncthreads();
     ht_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // this CTA's tile sequence: tile(i) = t0 + i * tstep for i in [0, n_my)
     const int G = gridDim.x;
+    int t0, tstep, n_my;
+    if (P.chunked) {
+        const int q = P.total_tiles / G, rem = P.total_tiles - q * G;
+        t0 = (int)blockIdx.x * q + min((int)blockIdx.x, rem);
+        n_my = q + ((int)blockIdx.x < rem ? 1 : 0);
+        tstep = 1;
+    } else {
+        t0 = blockIdx.x;
+        tstep = G;
+        n_my = (P.total_tiles - t0 + G - 1) / G;
+    }
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer
             int s = 0, cur = -1, r = 0;
             uint32_t ph = 0, wloads = 0;
-            for (int g = blockIdx.x; g < P.total_tiles; g += G) {
+            for (int i = 0; i < n_my; ++i) {
+                const int g = t0 + i * tstep;
                 r = ht_row_of(P, g, r);
                 const HtRow& R = P.row[r];
                 if (r != cur) {  // weights of a new (task, level): wait until the MMAs that read the old ones are done
@@ -218,7 +233,8 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
             // ------------------------------------------------ MMA issue: D1 in columns [0, 64) of a buffer, D2 in [64, 64 + ncp)
             int s = 0, cur = -1, r = 0, it = 0;
             uint32_t ph = 0, wloads = 0;
-            for (int g = blockIdx.x; g < P.total_tiles; g += G, ++it) {
+            for (; it < n_my; ++it) {
+                const int g = t0 + it * tstep;
                 r = ht_row_of(P, g, r);
                 const HtRow& R = P.row[r];
                 const int buf = it & 1;
@@ -250,8 +266,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
                         if (++s == S) { s = 0; ph ^= 1; }
                     }
                 }
-                const int gn = g + G;
-                if (gn >= P.total_tiles || ht_row_of(P, gn, r) != r) ht_commit(wempty);
+                if (it + 1 >= n_my || ht_row_of(P, g + tstep, r) != r) ht_commit(wempty);
                 ht_commit(tfull_bar(buf));
             }
         }
@@ -261,7 +276,8 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
         const int h = (warp - 2) >> 2;          // 0: sides l,r -> (cx, w) + even class chunks; 1: t,b -> (cy, h) + odd chunks
         const int etid = tid - 64;
         int cur = -1, r = 0, it = 0;
-        for (int g = blockIdx.x; g < P.total_tiles; g += G, ++it) {
+        for (; it < n_my; ++it) {
+            const int g = t0 + it * tstep;
             r = ht_row_of(P, g, r);
             const HtRow& R = P.row[r];
             if (r != cur) {  // biases of the new (task, level) as floats (all epilogue threads are between tiles here)
@@ -467,6 +483,9 @@ extern "C" int cerb_head_tail(const void* const* box_feat, const void* const* cl
         const int fixed = w2_bytes + w3_bytes + (64 + HT_MAX_NCP) * 4 + (2 * HT_MAX_STAGES + 8) * 8 + 1024 /* alignment slack */;
         int S = (smem_max - fixed) / P.stage_bytes;
         if (S > HT_MAX_STAGES) S = HT_MAX_STAGES;
+        int kv = 0;
+        if (cerb_debug_knob("ht_stages", &kv) && kv >= 2 && kv < S) S = kv;
+        P.chunked = cerb_debug_knob("ht_order", &kv) ? (kv != 0) : 1;
         if (S < 2) {
             cerb_set_error("cerb_head_tail: %d + %d weight bytes and %d-byte stages do not fit %d bytes of shared memory", w2_bytes, w3_bytes, P.stage_bytes, smem_max);
             return CERB_ENOSPC;

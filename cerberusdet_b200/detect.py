@@ -15,6 +15,7 @@ import torch
 from .ops import decode_heads
 
 _RAW_FLAG = "_cerb_raw_heads"  # set by inference.raw_heads(): return the per-level tensors undecoded
+_FUSE_FLAG = "_cerb_fuse_tail"  # set by inference.raw_heads(fuse=True): stop BEFORE the last 1x1 convolutions when possible
 _STRIDES_ATTR = "_cerb_strides"  # (key, python floats): the head's strides without a device sync per forward
 
 
@@ -49,6 +50,45 @@ class SplitHeads:
         self.box, self.cls = box, cls
 
 
+class FusedHeads:
+    """One task's head stopped one layer earlier still: ``box_feat[l]`` / ``cls_feat[l]`` are the INPUTS of the last 1x1
+    convolutions ``cv2[l][-1]`` / ``cv3[l][-1]`` (models/yolo.py:81-84); ``ops.head_tail`` runs those convolutions, the
+    concat and the decode in one tcgen05 kernel."""
+
+    __slots__ = ("box_feat", "cls_feat", "head")
+
+    def __init__(self, box_feat, cls_feat, head):
+        self.box_feat, self.cls_feat, self.head = box_feat, cls_feat, head
+
+    def to_split(self):
+        """Run the last convolutions the ordinary way (mixed batches of fusable and unfusable heads)."""
+        h = self.head
+        return SplitHeads([h.cv2[i][-1](f) for i, f in enumerate(self.box_feat)], [h.cv3[i][-1](f) for i, f in enumerate(self.cls_feat)])
+
+    def weights(self):
+        h = self.head
+        n = len(self.box_feat)
+        return ([h.cv2[i][-1].weight for i in range(n)], [h.cv2[i][-1].bias for i in range(n)],
+                [h.cv3[i][-1].weight for i in range(n)], [h.cv3[i][-1].bias for i in range(n)])
+
+
+def can_fuse_tail(head, x) -> bool:
+    """The fused kernel's preconditions (include/cerb_post.h: cerb_head_tail): half tensors, every level's H*W a multiple
+    of 8, both towers ending in a plain biased 1x1 ``nn.Conv2d`` whose input width is a multiple of 16, nc <= 192."""
+    if x[0].dtype != torch.float16 or head.nc > 192 or getattr(head, "reg_max", 16) != 16:
+        return False
+    for i in range(head.nl):
+        if (x[i].shape[2] * x[i].shape[3]) % 8:
+            return False
+        for seq, n_out in ((head.cv2[i], 64), (head.cv3[i], head.nc)):
+            last = seq[-1] if isinstance(seq, torch.nn.Sequential) and len(seq) > 1 else None
+            if not (isinstance(last, torch.nn.Conv2d) and last.kernel_size == (1, 1) and last.stride == (1, 1)
+                    and last.padding == (0, 0) and last.groups == 1 and last.bias is not None
+                    and last.out_channels == n_out and last.in_channels % 16 == 0 and last.weight.dtype == torch.float16):
+                return False
+    return True
+
+
 def detect_forward(self, x):
     """``forward(self, x: list[Tensor]) -> (y, x)`` | ``y`` (export) | ``x`` (training).
 
@@ -62,7 +102,11 @@ def detect_forward(self, x):
     shape = x[0].shape  # BCHW before the convs: the reference's anchor-cache key (yolo.py:88,93)
     if getattr(self, _RAW_FLAG, False):
         # inference engine: nobody reads the concatenated raw tensors, so the towers' outputs are handed over as they
-        # are and the decode kernel reads box and class channels from their own tensors (no torch.cat copy)
+        # are and the decode kernel reads box and class channels from their own tensors (no torch.cat copy) -- or, fused
+        # mode, the towers stop before their last 1x1 convolution and one kernel does the rest
+        if getattr(self, _FUSE_FLAG, False) and can_fuse_tail(self, x):
+            return None, FusedHeads([self.cv2[i][:-1](x[i]) for i in range(self.nl)],
+                                    [self.cv3[i][:-1](x[i]) for i in range(self.nl)], self)
         return None, SplitHeads([self.cv2[i](x[i]) for i in range(self.nl)], [self.cv3[i](x[i]) for i in range(self.nl)])
     x = _level_cat(self, x)
     if self.dynamic or self.shape != shape:

@@ -10,13 +10,14 @@ host code (``cross_task.py``), as in the reference.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 
 from . import cross_task
-from .detect import _RAW_FLAG, SplitHeads, head_strides
-from .ops import cross_task_merge, decode_heads, decode_heads_split, nms_batched
+from .detect import _FUSE_FLAG, _RAW_FLAG, FusedHeads, SplitHeads, head_strides
+from .ops import cross_task_merge, decode_heads, decode_heads_split, head_tail, nms_batched
 
 
 def _reference_nms():
@@ -31,17 +32,21 @@ def _reference_nms():
 
 
 @contextlib.contextmanager
-def raw_heads(model):
+def raw_heads(model, fuse: bool = False):
     """While active, patched Detect heads return ``(None, SplitHeads)`` -- the conv towers' outputs, not even
-    concatenated -- so that all task heads can be decoded together in one launch."""
+    concatenated -- so that all task heads can be decoded together in one launch.  ``fuse=True``: heads that meet the
+    fused kernel's preconditions (``detect.can_fuse_tail``) stop before their last 1x1 convolutions and return
+    ``(None, FusedHeads)`` instead."""
     heads = [m for m in model.modules() if hasattr(type(m), "_cerb_reference_forward")]
     for m in heads:
         setattr(m, _RAW_FLAG, True)
+        setattr(m, _FUSE_FLAG, bool(fuse))
     try:
         yield heads
     finally:
         for m in heads:
             setattr(m, _RAW_FLAG, False)
+            setattr(m, _FUSE_FLAG, False)
 
 
 class CerberusDetInference:
@@ -61,6 +66,9 @@ class CerberusDetInference:
         self.conf_thres = conf_thres
         self.iou_thres = iou_thres
         self.iou_thres_between_tasks = iou_thres_between_tasks
+        # extension: run the heads' last 1x1 convolutions inside the decode kernel (ops.head_tail) whenever the model
+        # is half and its shapes allow it; set to False to keep the convolutions in cuDNN
+        self.fuse_head_tail = os.environ.get("CERB_HEAD_TAIL", "1") != "0"
         if model is None:
             from . import patch
 
@@ -113,7 +121,7 @@ class CerberusDetInference:
         between = self.iou_thres_between_tasks if iou_thres_between_tasks is None else iou_thres_between_tasks
 
         # 1. forward: every head hands over its raw per-level tensors
-        with raw_heads(self.model):
+        with raw_heads(self.model, fuse=self.fuse_head_tail):
             all_out = self.model(tensor)
         # task order = the order of self.names (categories_inds_map), which is the order the reference's
         # nms_between_tasks regroups the rows in (utils/general.py:497-505) -- the scan below is order-dependent
@@ -121,7 +129,14 @@ class CerberusDetInference:
         preds = [all_out[t][0] for t in tasks]
         if any(p is None for p in preds):  # raw mode was honoured: decode all heads in one launch
             levels = [all_out[t][1] for t in tasks]
-            if all(isinstance(lv, SplitHeads) for lv in levels):  # patched heads: no channel concat was made
+            if any(isinstance(lv, FusedHeads) for lv in levels) and not all(isinstance(lv, FusedHeads) for lv in levels):
+                levels = [lv.to_split() if isinstance(lv, FusedHeads) else lv for lv in levels]
+            if all(isinstance(lv, FusedHeads) for lv in levels):  # last 1x1 convs + concat + decode in one kernel
+                strides = self._head_strides(len(levels[0].box_feat))
+                w = [lv.weights() for lv in levels]
+                preds = head_tail([lv.box_feat for lv in levels], [lv.cls_feat for lv in levels], [x[0] for x in w],
+                                  [x[1] for x in w], [x[2] for x in w], [x[3] for x in w], strides)
+            elif all(isinstance(lv, SplitHeads) for lv in levels):  # patched heads: no channel concat was made
                 strides = self._head_strides(len(levels[0].box))
                 preds = decode_heads_split([lv.box for lv in levels], [lv.cls for lv in levels], strides)
             else:

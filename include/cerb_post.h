@@ -226,7 +226,8 @@ int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_row
  * on a knob: the parity tests run the alternatives against each other.  Knobs: "decode_pipe" (0 = register-resident
  * decode kernel instead of the pipelined one), "decode_order", "decode_vec", "decode_l2hint", "nms_minb" (1 | 2: the
  * 128- / 64-register NMS build), "nms_pdl" (0 = no programmatic dependent launch), "chunk_cap", "chunk_first",
- * "hist_sample".
+ * "hist_sample", "ht_order" (head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = contiguous runs), "ht_stages"
+ * (cap on its activation ring depth).
  */
 int cerb_debug_set(const char* name, int value);
 int cerb_debug_reset(void);
