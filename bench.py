@@ -404,14 +404,15 @@ def main():
     # N > 1: the NMS kernel writes each batch's padded detections where the delivery to rank 0 picks them up: straight
     # into rank 0's memory over NVLink (peer-mapped symmetric memory) or, failing that, into a packed local buffer that
     # one asynchronous NCCL gather moves.  Two buffers alternate with the pipeline's two output slots.
-    delivery = make_delivery(len(NCS), B_PER_GPU, NMS_KW["max_det"], dev) if world > 1 else None
+    delivery = make_delivery(len(NCS), B_PER_GPU, NMS_KW["max_det"], dev, prefer_peer=not args.serial) if world > 1 else None
     outs = delivery.outs if delivery is not None else None
 
     steps = args.steps
     # instrumented steps: parity must match the step index; spread evenly over the timed region, never step 0
     n_timed = 0 if args.serial else min(TIMED_SLOTS if steps >= 128 else 16, max(steps - 1, 0))
     timed_at = sorted({1 + (i * (steps - 1)) // n_timed for i in range(n_timed)}) if n_timed else []
-    pipe = PostHeadPipeline(heads_dev, STRIDES, NMS_KW, outs=outs, timed_parities=[k & 1 for k in timed_at], overlap=not args.serial)
+    pipe = PostHeadPipeline(heads_dev, STRIDES, NMS_KW, outs=outs, timed_parities=[k & 1 for k in timed_at], overlap=not args.serial,
+                            delivery=delivery)
     slot_of = {k: i for i, k in enumerate(timed_at)}
 
     def run_steps(n, timed=False):
@@ -502,7 +503,7 @@ def main():
         b5 = 512 // world
         heads5 = [[x.repeat(b5 // B_PER_GPU, 1, 1, 1) if b5 >= B_PER_GPU else x[:b5].contiguous() for x in lv] for lv in heads_dev]
         deliv5 = make_delivery(len(NCS), b5, NMS_KW["max_det"], dev) if world > 1 else None
-        pipe5 = PostHeadPipeline(heads5, STRIDES, NMS_KW, outs=deliv5.outs if deliv5 else None)
+        pipe5 = PostHeadPipeline(heads5, STRIDES, NMS_KW, outs=deliv5.outs if deliv5 else None, delivery=deliv5)
         s5 = 40
 
         def run5(n):

@@ -24,6 +24,8 @@ EXPORTS = (
     "cerb_nms_workspace_bytes",
     "cerb_nms",
     "cerb_nms_stats",
+    "cerb_nms_deliver",
+    "cerb_deliver_collect",
     "cerb_decode_nms",
     "cerb_cross_task",
     "cerb_cross_task_workspace_bytes",
@@ -77,6 +79,11 @@ def load() -> ctypes.CDLL:
     if hasattr(lib, "cerb_nms_stats") or "CERB_LIB" not in os.environ:
         lib.cerb_nms_stats.restype = i
         lib.cerb_nms_stats.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp, vp]
+    if hasattr(lib, "cerb_nms_deliver") or "CERB_LIB" not in os.environ:
+        lib.cerb_nms_deliver.restype = i
+        lib.cerb_nms_deliver.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp, vp, vp, vp, vp]
+        lib.cerb_deliver_collect.restype = i
+        lib.cerb_deliver_collect.argtypes = [vp, vpp, vp, i, i, vp]
     lib.cerb_decode_nms.restype = i
     lib.cerb_decode_nms.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_cross_task.restype = i

@@ -26,14 +26,16 @@ enum Knob {
     K_HIST_SAMPLE,    // stride of the estimating histogram
     K_HT_ORDER,       // head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = one contiguous run of tiles per CTA
     K_HT_STAGES,      // head-tail kernel: cap on the activation ring depth (2..8)
+    K_HT_GROUPS,      // head-tail kernel: epilogue groups (1 | 2)
     K_COUNT
 };
 static const char* const kKnobName[K_COUNT] = {"decode_pipe", "decode_order", "decode_vec", "decode_l2hint", "nms_minb",
                                                "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample",  "ht_order",
-                                               "ht_stages"};
+                                               "ht_stages",   "ht_groups"};
 static const char* const kKnobEnv[K_COUNT] = {"CERB_DEBUG_DECODE_PIPE", "CERB_DEBUG_DECODE_ORDER", "CERB_DEBUG_DECODE_VEC",
                                               "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL",
-                                              nullptr, nullptr, nullptr, "CERB_DEBUG_HT_ORDER", "CERB_DEBUG_HT_STAGES"};
+                                              nullptr, nullptr, nullptr, "CERB_DEBUG_HT_ORDER", "CERB_DEBUG_HT_STAGES",
+                                              "CERB_DEBUG_HT_GROUPS"};
 struct KnobTable {
     int v[K_COUNT];
     bool set[K_COUNT];
@@ -254,10 +256,65 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
                           max_nms, max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, stream);
 }
 
+struct NmsDelivery {
+    void* flag;
+    const void* ack;
+    void* seq;
+    void* done;
+};
+static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres, double iou_thres,
+                    const int* classes, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, double max_wh,
+                    const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes,
+                    unsigned long long* stats, const NmsDelivery* dv, void* stream);
+
 extern "C" int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                               double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
                               int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts,
                               void* workspace, size_t workspace_bytes, unsigned long long* stats, void* stream) {
+    return nms_impl(pred, nc, T, B, A, dtype, conf_thres, iou_thres, classes, n_classes, agnostic, multi_label, max_det, max_nms,
+                    max_wh, smax, dets, counts, workspace, workspace_bytes, stats, nullptr, stream);
+}
+
+extern "C" int cerb_nms_deliver(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+                                double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
+                                int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts,
+                                void* workspace, size_t workspace_bytes, void* flag_remote, const void* ack_local,
+                                void* seq_local, void* done_local, void* stream) {
+    REQUIRE(flag_remote && ack_local && seq_local && done_local, "cerb_nms_deliver: null delivery pointer");
+    REQUIRE(aligned_to(flag_remote, 4) && aligned_to(ack_local, 4) && aligned_to(seq_local, 4) && aligned_to(done_local, 4),
+            "cerb_nms_deliver: delivery words must be 4-byte aligned");
+    const NmsDelivery dv = {flag_remote, ack_local, seq_local, done_local};
+    return nms_impl(pred, nc, T, B, A, dtype, conf_thres, iou_thres, classes, n_classes, agnostic, multi_label, max_det, max_nms,
+                    max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, &dv, stream);
+}
+
+extern "C" int cerb_deliver_collect(const void* flags_local, void* const* ack_remote, void* collected_local, int world, int dst,
+                                    void* stream) {
+    g_err[0] = 0;
+    REQUIRE(flags_local && ack_remote && collected_local, "cerb_deliver_collect: null argument");
+    REQUIRE(world >= 1 && world <= CERB_MAX_RANKS && dst >= 0 && dst < world, "cerb_deliver_collect: world=%d dst=%d (at most %d ranks)", world, dst, CERB_MAX_RANKS);
+    CollectParams P;
+    memset(&P, 0, sizeof(P));
+    P.flags = (const unsigned*)flags_local;
+    P.collected = (unsigned*)collected_local;
+    P.world = world;
+    P.dst = dst;
+    for (int r = 0; r < world; ++r) {
+        REQUIRE(r == dst || ack_remote[r] != nullptr, "cerb_deliver_collect: ack_remote[%d] is null", r);
+        P.ack[r] = (unsigned*)ack_remote[r];
+    }
+    cudaError_t e = cerb_launch_deliver_collect(P, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_deliver_collect: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
+}
+
+static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres, double iou_thres,
+                    const int* classes, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, double max_wh,
+                    const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes,
+                    unsigned long long* stats, const NmsDelivery* dv, void* stream) {
     g_err[0] = 0;
     REQUIRE(pred && nc, "cerb_nms: null argument");
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_nms: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
@@ -307,6 +364,12 @@ extern "C" int cerb_nms_stats(const void* const* pred, const int* nc, int T, int
     P.dets = dets;
     P.counts = counts;
     P.pair_counts = stats;
+    if (dv != nullptr) {
+        P.deliver_flag = (unsigned*)dv->flag;
+        P.deliver_ack = (const unsigned*)dv->ack;
+        P.deliver_seq = (unsigned*)dv->seq;
+        P.deliver_done = (unsigned*)dv->done;
+    }
     const size_t need = cerb_nms_kept_ws_bytes(T, B, max_det);
     if (need) {
         if (workspace == nullptr || workspace_bytes < need) {

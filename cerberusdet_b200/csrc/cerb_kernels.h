@@ -55,8 +55,25 @@ struct NmsParams {
     unsigned long long* pair_counts;  // optional [T*B][2]: IoU tests made, candidates consumed (statistics), else null
     int force_minb;         // host only: 0 = pick the register build per launch, 1 / 2 = force it (tests, tools)
     int pdl;                // host only: launch with programmatic stream serialization (default 1)
+    // Multi-GPU delivery without a collective (shard.py: PeerDelivery): `dets` / `counts` point into rank dst's
+    // peer-mapped memory; the kernel itself tells dst when the batch is complete and waits for dst before it reuses the
+    // slot.  All four null = off.
+    unsigned* deliver_flag;        // dst's memory (peer-mapped): batches this rank has delivered into this slot
+    const unsigned* deliver_ack;   // local, written remotely by dst: batches dst has taken out of this slot
+    unsigned* deliver_seq;         // local: batches this rank has written into this slot (kept by the kernel)
+    unsigned* deliver_done;        // local: CTA completion counter of the running launch (zero between launches)
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
+// dst's side of the delivery: one CTA; thread r waits until rank r's flag reaches (*collected + 1), then acknowledges
+// into rank r's memory (ack[r], peer-mapped); *collected is advanced at the end
+#define CERB_MAX_RANKS 16
+struct CollectParams {
+    const unsigned* flags;            // local [world]
+    unsigned* ack[CERB_MAX_RANKS];    // peer-mapped, entry dst unused
+    unsigned* collected;              // local counter of this slot
+    int world, dst;
+};
+cudaError_t cerb_launch_deliver_collect(const CollectParams& P, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);
 
 // ------------------------------------------------------------------ cross-task merge

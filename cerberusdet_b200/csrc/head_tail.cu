@@ -18,23 +18,29 @@
 // B (weights [N][K] row-major = K-major): TMA boxes {64 k, N rows}, SWIZZLE_128B -> the K-major SW128 image (row n at
 //   n*128 B inside a 64-wide K block, 16-byte chunks XOR-swizzled by n & 7), SBO = 1024 B; a K = 16 step advances the
 //   start address by 32 B inside the swizzled row.  Rows >= nc and columns >= K are zero-filled by TMA.
-// D: TMEM, lane = anchor, column = output channel, two accumulator buffers (tile i+1 is multiplied while tile i is
-//   decoded).  tcgen05.ld.32x32b hands each epilogue thread the logits of ITS anchor, so the epilogue is the per-anchor
+// D: TMEM, lane = anchor, column = output channel, up to four accumulator buffers (tiles i+1.. are multiplied while
+//   tile i is decoded).  tcgen05.ld.32x32b hands each epilogue thread the logits of ITS anchor, so the epilogue is the per-anchor
 //   decode math of decode.cu after "conv output = half(acc + bias)".
 //
-// Warp roles (320 threads, 1 CTA per SM): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one
-// lane), warps 2-9 = epilogue: two warps per TMEM lane quadrant, the first takes DFL sides l,r (x axis) and the even
-// 8-class chunks, the second sides t,b (y axis) and the odd chunks.
+// Warp roles (576 threads, 1 CTA per SM): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one
+// lane), warps 2-17 = epilogue in two groups of 8 that take alternate tiles; inside a group two warps per TMEM lane
+// quadrant, the first takes DFL sides l,r (x axis) and the even 8-class chunks, the second sides t,b (y axis) and the
+// odd chunks.
 // Pipelines: activation ring full[s]/empty[s] (TMA -> MMA -> TMA), weights wfull/wempty (reloaded when the CTA's tile
-// sequence enters another (task, level)), accumulators tfull[2]/tempty[2] (MMA -> epilogue -> MMA).
+// sequence enters another (task, level)), accumulators tfull[b]/tempty[b] over up to 4 TMEM buffers (MMA -> epilogue
+// -> MMA).
 #include <cuda.h>
 
 #include "../../include/cerb_post.h"
 #include "decode_common.cuh"
 
 #define HT_TILE 128
-#define HT_EPI_WARPS 8
-#define HT_THREADS (64 + 32 * HT_EPI_WARPS)
+#define HT_EPI_WARPS 8    // epilogue warps per group: two per TMEM lane quadrant
+#define HT_EPI_GROUPS 2   // at most; groups take alternate tiles.  One group decodes a tile in ~2.9 us, which is slower than
+                          // the memory stream delivers one below ~384 input channels: the host launches 2 groups
+                          // there and 1 above (profiles/r02_head_tail.md)
+#define HT_MAX_BUFS 4     // TMEM accumulator buffers (as many as fit 512 columns, at least 2)
+#define HT_THREADS (64 + 32 * HT_EPI_WARPS * HT_EPI_GROUPS)
 #define HT_MAX_ROWS 12   // (task, level) pairs per launch; more are split over several launches
 #define HT_MAX_STAGES 8
 #define HT_MAX_NCP 192   // two accumulator buffers of 64 + NCP columns must fit the 512 TMEM columns
@@ -56,7 +62,8 @@ struct HeadTailParams {
     int nrows, total_tiles, B, A;
     int nstages, stage_bytes;
     int off_w2, off_w3, off_bias, off_bar;  // byte offsets inside the (1024-aligned) dynamic shared memory
-    int tmem_cols, buf_cols;
+    int tmem_cols, buf_cols, nbufs;
+    int ngroups;                            // epilogue groups launched (blockDim = 64 + 256 * ngroups)
     int srow;                               // score-summary row length (cerb_summary_row_len)
     int chunked;                            // 1: CTA i owns one contiguous run of tiles (few (task, level) changes, so few
                                             // weight reloads); 0: tiles dealt round-robin
@@ -84,6 +91,22 @@ __device__ __forceinline__ void ht_mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!ok);
+}
+// the same with a pause between polls: the 8-16 epilogue warps wait here for most of a memory-bound tile and must
+// not take issue slots from the single producer / MMA lanes
+__device__ __forceinline__ void ht_mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(40);
+    }
 }
 #define HT_EVICT_FIRST 0x12F0000000000000ull  // L2 cache-hint encodings (CUTLASS cute/arch/copy_sm90_tma.hpp)
 #define HT_EVICT_LAST 0x14F0000000000000ull
@@ -152,22 +175,23 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
     const int S = P.nstages;
     unsigned char* const sW2 = smem + P.off_w2;
     unsigned char* const sW3 = smem + P.off_w3;
-    float* const sbias = reinterpret_cast<float*>(smem + P.off_bias);  // [64 + HT_MAX_NCP]
+    float* const sbias_all = reinterpret_cast<float*>(smem + P.off_bias);  // [HT_EPI_GROUPS][64 + HT_MAX_NCP]
     uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + P.off_bar);
-    // barrier map: full[0..S), empty[S..2S), wfull, wempty, tfull[2], tempty[2], then the TMEM base address slot
+    // barrier map: full[0..S), empty[S..2S), wfull, wempty, tfull[HT_MAX_BUFS], tempty[HT_MAX_BUFS], then the TMEM base address slot
     const uint32_t bar0 = ht_smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
     const uint32_t wfull = bar0 + 8u * (2 * S), wempty = wfull + 8u;
     auto tfull_bar = [&](int b) { return wfull + 16u + 8u * b; };
-    auto tempty_bar = [&](int b) { return wfull + 32u + 8u * b; };
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
+    auto tempty_bar = [&](int b) { return wfull + 16u + 8u * (HT_MAX_BUFS + b); };
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 + 2 * HT_MAX_BUFS);
+    const int NB = P.nbufs;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ht_mbar_init(full_bar(s), 1); ht_mbar_init(empty_bar(s), 1); }
         ht_mbar_init(wfull, 1);
         ht_mbar_init(wempty, 1);
-        for (int b = 0; b < 2; ++b) { ht_mbar_init(tfull_bar(b), 1); ht_mbar_init(tempty_bar(b), HT_EPI_WARPS); }
+        for (int b = 0; b < HT_MAX_BUFS; ++b) { ht_mbar_init(tfull_bar(b), 1); ht_mbar_init(tempty_bar(b), HT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: one warp allocates, the base address lands in shared memory
@@ -237,8 +261,8 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
                 const int g = t0 + it * tstep;
                 r = ht_row_of(P, g, r);
                 const HtRow& R = P.row[r];
-                const int buf = it & 1;
-                ht_mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+                const int buf = it % NB;
+                ht_mbar_wait(tempty_bar(buf), ((it / NB) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
                 if (r != cur) {
                     ht_mbar_wait(wfull, wloads & 1);
                     ++wloads;
@@ -273,28 +297,30 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
     } else {
         // ------------------------------------------------ epilogue: thread = TMEM lane = anchor
         const int q = warp & 3;                 // a warp may only read the TMEM lane quadrant warp % 4
-        const int h = (warp - 2) >> 2;          // 0: sides l,r -> (cx, w) + even class chunks; 1: t,b -> (cy, h) + odd chunks
-        const int etid = tid - 64;
-        int cur = -1, r = 0, it = 0;
-        for (; it < n_my; ++it) {
+        const int grp = (warp - 2) / HT_EPI_WARPS;  // epilogue group: takes the tiles it = grp, grp + HT_EPI_GROUPS, ...
+        const int h = ((warp - 2) >> 2) & 1;    // 0: sides l,r -> (cx, w) + even class chunks; 1: t,b -> (cy, h) + odd chunks
+        const int etid = tid - 64 - grp * 32 * HT_EPI_WARPS;
+        float* const sbias = sbias_all + grp * (64 + HT_MAX_NCP);
+        int cur = -1, r = 0, it = grp;
+        for (; it < n_my; it += P.ngroups) {
             const int g = t0 + it * tstep;
             r = ht_row_of(P, g, r);
             const HtRow& R = P.row[r];
             if (r != cur) {  // biases of the new (task, level) as floats (all epilogue threads are between tiles here)
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * HT_EPI_WARPS) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * HT_EPI_WARPS) : "memory");
                 for (int i = etid; i < 64 + R.ncp; i += 32 * HT_EPI_WARPS)
                     sbias[i] = i < 64 ? __half2float(R.b2[i]) : (i - 64 < R.nc ? __half2float(R.b3[i - 64]) : 0.f);
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * HT_EPI_WARPS) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * HT_EPI_WARPS) : "memory");
                 cur = r;
             }
             const int lt = g - R.tile_start;
             const int b = lt / R.tiles_per_image;
             const int a = (lt - b * R.tiles_per_image) * HT_TILE + q * 32 + lane;  // anchor inside the level
             const bool live = a < R.hw;
-            const int buf = it & 1;
+            const int buf = it % NB;
             const uint32_t trow = tmem + (uint32_t)buf * P.buf_cols + ((uint32_t)(q * 32) << 16);
             __half* __restrict__ yb = R.y + (size_t)b * (4 + R.nc) * P.A + R.aoff + a;
-            ht_mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+            ht_mbar_wait_backoff(tfull_bar(buf), (it / NB) & 1);
             ht_fence_after();
             {   // DFL sides h and h + 2 of this anchor -> centre and size on axis h (tal.py:198-204, yolo.py:98)
                 uint32_t r0[16], r1[16];
@@ -317,7 +343,14 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
                     yb[(size_t)(h + 2) * P.A] = os.e[0];
                 }
             }
-            for (int c0 = h * 8; c0 < R.nc; c0 += 16) {  // class sigmoids (yolo.py:99) + score summary
+            // class sigmoids (yolo.py:99) + score summary; addresses advance by pointer, nothing is multiplied per class
+            const size_t Astr = (size_t)P.A;
+            __half* __restrict__ ycls = yb + 4 * Astr + (size_t)(h * 8) * Astr;
+            const bool sm_on = R.smax != nullptr;
+            __half* __restrict__ smp = sm_on ? R.smax + ((size_t)b * R.nc + h * 8) * P.srow + ((R.aoff + a) >> 3) : nullptr;
+            const bool sm_writer = sm_on && live && (lane & 7) == 0;
+            const float* __restrict__ bcls = sbias + 64;
+            for (int c0 = h * 8; c0 < R.nc; c0 += 16, ycls += 16 * Astr, smp += 16 * (size_t)P.srow) {
                 uint32_t rc[8];
                 ht_tmem_ld8(trow + 64 + c0, rc);
                 ht_tmem_wait();
@@ -325,23 +358,23 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tail_kernel(const __grid_c
                 for (int k = 0; k < 8; k += 2) {
                     const int c = c0 + k;
                     if (c < R.nc) {  // (warp-uniform)
+                        const bool two = c + 1 < R.nc;
                         float l0, l1;
-                        rnd2<__half>(__uint_as_float(rc[k]) + sbias[64 + c], __uint_as_float(rc[k + 1]) + sbias[64 + c + 1], l0, l1);
+                        rnd2<__half>(__uint_as_float(rc[k]) + bcls[c], __uint_as_float(rc[k + 1]) + bcls[c + 1], l0, l1);
                         const float2 sg = sigmoid2(make_float2(l0, l1));
                         const __half2 s2 = __floats2half2_rn(sg.x, sg.y);
                         if (live) {
-                            yb[(size_t)(4 + c) * P.A] = __low2half(s2);
-                            if (c + 1 < R.nc) yb[(size_t)(5 + c) * P.A] = __high2half(s2);
+                            ycls[k * Astr] = __low2half(s2);
+                            if (two) ycls[(k + 1) * Astr] = __high2half(s2);
                         }
-                        if (R.smax != nullptr) {  // maximum over the 8 anchors of a 16-byte score vector (decode_pipe.cu)
+                        if (sm_on) {  // maximum over the 8 anchors of a 16-byte score vector (decode_pipe.cu)
                             __half2 m = live ? s2 : __floats2half2_rn(0.f, 0.f);
                             m = __hmax2(m, __shfl_xor_sync(0xffffffffu, m, 1));
                             m = __hmax2(m, __shfl_xor_sync(0xffffffffu, m, 2));
                             m = __hmax2(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                            if ((lane & 7) == 0 && live) {
-                                __half* sm = R.smax + ((size_t)b * R.nc + c) * P.srow + (R.aoff + a) / 8;
-                                sm[0] = __low2half(m);
-                                if (c + 1 < R.nc) sm[P.srow] = __high2half(m);
+                            if (sm_writer) {
+                                smp[k * (size_t)P.srow] = __low2half(m);
+                                if (two) smp[(k + 1) * (size_t)P.srow] = __high2half(m);
                             }
                         }
                     }
@@ -478,14 +511,21 @@ extern "C" int cerb_head_tail(const void* const* box_feat, const void* const* cl
         P.stage_bytes = stage_rows * 256;
         P.srow = (int)cerb_summary_row_len(A, CERB_F16);
         P.buf_cols = 64 + ncp_max;
+        P.nbufs = 512 / P.buf_cols;  // >= 2 because ncp <= HT_MAX_NCP
+        if (P.nbufs > HT_MAX_BUFS) P.nbufs = HT_MAX_BUFS;
         P.tmem_cols = 32;
-        while (P.tmem_cols < 2 * P.buf_cols) P.tmem_cols <<= 1;
-        const int fixed = w2_bytes + w3_bytes + (64 + HT_MAX_NCP) * 4 + (2 * HT_MAX_STAGES + 8) * 8 + 1024 /* alignment slack */;
+        while (P.tmem_cols < P.nbufs * P.buf_cols) P.tmem_cols <<= 1;
+        const int bias_bytes = HT_EPI_GROUPS * (64 + HT_MAX_NCP) * 4, bar_bytes = (2 * HT_MAX_STAGES + 2 + 2 * HT_MAX_BUFS + 2) * 8;
+        const int fixed = w2_bytes + w3_bytes + bias_bytes + bar_bytes + 1024 /* alignment slack */;
         int S = (smem_max - fixed) / P.stage_bytes;
         if (S > HT_MAX_STAGES) S = HT_MAX_STAGES;
         int kv = 0;
         if (cerb_debug_knob("ht_stages", &kv) && kv >= 2 && kv < S) S = kv;
         P.chunked = cerb_debug_knob("ht_order", &kv) ? (kv != 0) : 1;
+        int min_ch = 1 << 30;
+        for (int i = 0; i < P.nrows; ++i) min_ch = min(min_ch, P.row[i].c2 + P.row[i].c3);
+        P.ngroups = min_ch >= 384 ? 1 : HT_EPI_GROUPS;
+        if (cerb_debug_knob("ht_groups", &kv) && kv >= 1 && kv <= HT_EPI_GROUPS) P.ngroups = kv;
         if (S < 2) {
             cerb_set_error("cerb_head_tail: %d + %d weight bytes and %d-byte stages do not fit %d bytes of shared memory", w2_bytes, w3_bytes, P.stage_bytes, smem_max);
             return CERB_ENOSPC;
@@ -494,8 +534,8 @@ extern "C" int cerb_head_tail(const void* const* box_feat, const void* const* cl
         P.off_w2 = S * P.stage_bytes;
         P.off_w3 = P.off_w2 + w2_bytes;
         P.off_bias = P.off_w3 + w3_bytes;
-        P.off_bar = P.off_bias + (64 + HT_MAX_NCP) * 4;
-        int smem = P.off_bar + (2 * S + 8) * 8 + 1024;
+        P.off_bar = P.off_bias + bias_bytes;
+        int smem = P.off_bar + bar_bytes + 1024;
         if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM whatever the model width (the TMEM allocation assumes it)
         if (want_summary && P.srow == 0) {
             cerb_set_error("cerb_head_tail: the score summary needs A %% 8 == 0 (A=%d)", A);
@@ -503,7 +543,7 @@ extern "C" int cerb_head_tail(const void* const* box_feat, const void* const* cl
         }
         cudaError_t e = cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) {
-            head_tail_kernel<<<min(tiles, sms), HT_THREADS, smem, (cudaStream_t)stream>>>(P);
+            head_tail_kernel<<<min(tiles, sms), 64 + 32 * HT_EPI_WARPS * P.ngroups, smem, (cudaStream_t)stream>>>(P);
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) {

@@ -683,6 +683,15 @@ template <int E> __device__ __forceinline__ void block_sort_desc(u64* keys) {
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // MINB = CTAs per SM the registers are budgeted for: 2 (64 registers; needed when there are more segments than SMs) or
 // 1 (128 registers, no spills: 26 % faster per segment, used when every segment gets an SM of its own -- cerb_launch_nms)
 template <typename T, bool MULTI, int MINB>
@@ -758,6 +767,12 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     // Programmatic dependent launch: this grid may have been started while the kernel before it in the stream (the
     // decode kernel) was still draining; nothing above touched global memory.  Wait for that kernel's results here.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.deliver_flag != nullptr && tid == 0) {
+        // the output slot lives in rank dst's memory: dst must have taken the batch this rank wrote there last time
+        // (two batches ago, so this never spins in steady state).  Bounded: a lost peer must not hang the GPU.
+        const unsigned need = *reinterpret_cast<volatile unsigned*>(P.deliver_seq);
+        for (unsigned spins = 0; ld_acquire_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+    }  // (every path below passes a __syncthreads before the first store to dets)
     if (smax) build_hist_summary(); else build_hist(hstride, NMS_BINS);
     PROF(1);  // first histogram
 
@@ -1105,9 +1120,40 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     }
     // rows past the count are zero so the padded [T, B, max_det, 6] output is deterministic without a separate fill
     for (int i = kept * 6 + tid; i < max_det * 6; i += NMS_THREADS) dets[i] = 0.f;
+    if (P.deliver_flag != nullptr) {
+        // tell rank dst that this rank's batch is complete: every CTA publishes its (remote) stores system-wide and
+        // counts itself; the last one bumps the slot's sequence number and releases it into dst's flag
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (atomicAdd(P.deliver_done, 1u) == gridDim.x - 1) {
+                *reinterpret_cast<volatile unsigned*>(P.deliver_done) = 0u;
+                const unsigned n = *reinterpret_cast<volatile unsigned*>(P.deliver_seq) + 1u;
+                *reinterpret_cast<volatile unsigned*>(P.deliver_seq) = n;
+                __threadfence_system();
+                st_release_sys(P.deliver_flag, n);
+            }
+        }
+    }
     PROF(9);  // rest
     PROF_FLUSH(consumed);
     BLOCK_T_END
+}
+
+// rank dst's side of the peer delivery (cerb_kernels.h: CollectParams)
+__global__ void deliver_collect_kernel(const __grid_constant__ CollectParams P) {
+    const int r = threadIdx.x;
+    const unsigned need = *reinterpret_cast<volatile unsigned*>(P.collected) + 1u;
+    if (r < P.world && r != P.dst) {
+        for (unsigned spins = 0; ld_acquire_sys(P.flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
+        st_release_sys(P.ack[r], need);
+    }
+    __syncthreads();
+    if (r == 0) *reinterpret_cast<volatile unsigned*>(P.collected) = need;
+}
+cudaError_t cerb_launch_deliver_collect(const CollectParams& P, cudaStream_t stream) {
+    deliver_collect_kernel<<<1, 32, 0, stream>>>(P);
+    return cudaGetLastError();
 }
 
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det) {

@@ -185,7 +185,10 @@ def _nms_impl(
     smax: Sequence[torch.Tensor],
     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     stats: Optional[torch.Tensor] = None,
+    deliver: Optional[Tuple[int, int, int, int]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``deliver`` = device addresses ``(flag_remote, ack_local, seq_local, done_local)`` of the multi-GPU delivery
+    protocol (``cerb_nms_deliver``; shard.PeerDelivery owns the words), ``out`` then lives in rank dst's memory."""
     lib = _lib.load()
     T = len(preds)
     first = preds[0]
@@ -221,15 +224,18 @@ def _nms_impl(
             sm_arr = _lib.ptr_array([s.data_ptr() for s in smax])
     if stats is not None and (stats.dtype != torch.int64 or tuple(stats.shape) != (T, B, 2) or stats.device != dev or not stats.is_contiguous()):
         raise ValueError("stats must be a contiguous int64 [T, B, 2] tensor on the input device")
-    with torch.cuda.device(dev):
-        rc = lib.cerb_nms_stats(
-            _lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
+    head = (_lib.ptr_array([p.data_ptr() for p in ps]), _lib.int_array(ncs), T, B, A, code,
             float(conf_thres), float(iou_thres), cls_arr, len(classes) if classes is not None else 0,
             int(bool(agnostic)), int(bool(multi_label)), int(max_det), int(max_nms), float(max_wh),
             sm_arr,
-            dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
-            stats.data_ptr() if stats is not None else None, _stream_ptr(dev),
-        )
+            dets.data_ptr(), counts.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes)
+    with torch.cuda.device(dev):
+        if deliver is not None:
+            if stats is not None or out is None:
+                raise ValueError("deliver= needs out= (the peer-mapped slot) and excludes stats=")
+            rc = lib.cerb_nms_deliver(*head, *[int(a) for a in deliver], _stream_ptr(dev))
+        else:
+            rc = lib.cerb_nms_stats(*head, stats.data_ptr() if stats is not None else None, _stream_ptr(dev))
     _lib.check(rc)
     return dets, counts
 
@@ -495,6 +501,7 @@ def nms_batched(
     max_wh: float = MAX_WH,
     use_summary: bool = True,
     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    deliver: Optional[Tuple[int, int, int, int]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """All task heads, all images, one launch.  Returns padded ``dets[T,B,max_det,6]`` and
     ``counts[T,B]`` (device tensors; no host sync).  Predictions that came out of ``decode_heads``
@@ -511,6 +518,8 @@ def nms_batched(
             smax = found
     args = (preds, float(conf_thres), float(iou_thres), None if classes is None else [int(c) for c in classes],
             bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)
+    if deliver is not None:  # multi-GPU: out is a slot in rank dst's memory, the kernel runs the delivery protocol itself
+        return _nms_impl(*args, out=out, deliver=deliver)
     if out is not None:
         nms_out_op(*args, out[0], out[1])
         return out

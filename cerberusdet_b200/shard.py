@@ -118,6 +118,7 @@ class GatherDelivery:
     (``DetectionGatherer``), two alternating buffers.  Works on every backend (NCCL on GPUs, gloo in the CPU tests)."""
 
     kind = "one asynchronous gather per batch (torch.distributed)"
+    in_graph = False
 
     def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
         self.g = [DetectionGatherer(T, b_loc, max_det, device, dst=dst, group=group) for _ in range(2)]
@@ -138,34 +139,54 @@ class GatherDelivery:
     def result(self, slot: int):
         return self.g[slot].result()
 
+    def nms_deliver_args(self, slot: int):
+        return None
+
+    def collect(self, slot: int) -> None:
+        pass
+
 
 class PeerDelivery:
-    """Per-batch delivery WITHOUT a collective on the data path: every rank's NMS kernel writes its padded detections
-    straight into rank ``dst``'s memory over NVLink -- ``outs[slot]`` on rank r are views of rank dst's symmetric-memory
-    buffer (``torch.distributed._symmetric_memory``: peer-mapped device memory), region (slot, r).  What remains per batch
-    is one flag per rank: the writer signals "slot filled" after its kernel, ``dst`` acknowledges once it has seen every
-    rank's flag, and a writer waits for that acknowledgement before it reuses the slot (two batches later, so in steady
-    state it never blocks).  No NCCL kernel takes SMs from the next batch's decode, no stream waits for a gather.
+    """Per-batch delivery WITHOUT a collective and without a single extra launch on the writers: every rank's NMS kernel
+    writes its padded detections straight into rank ``dst``'s memory over NVLink -- ``outs[slot]`` on rank r are views of
+    rank dst's symmetric-memory buffer (``torch.distributed._symmetric_memory``: peer-mapped device memory), region
+    (slot, r) -- and runs the hand-shake itself (``cerb_nms_deliver``, include/cerb_post.h):
 
-    The NMS kernel only ever writes ``dets`` / ``counts`` (24-byte rows, the zero fill of unused rows, one count per
-    segment); remote stores are posted, and their visibility to ``dst`` is ordered by the kernel boundary before the
-    flag (stream order on the writer, acquire on the reader's wait)."""
+      * its last CTA, after every CTA has fenced its remote stores, releases the slot's batch count into dst's flag word;
+      * before its first store it checks that dst has acknowledged the batch it wrote into this slot two batches ago.
 
-    kind = "NMS kernel stores straight into rank 0's peer-mapped symmetric memory over NVLink + one flag per rank and batch"
+    Rank ``dst`` runs one 32-thread kernel per batch (``collect(slot)`` -> ``cerb_deliver_collect``): thread r waits for
+    rank r's flag and stores the acknowledgement into rank r's memory.  All of it is stream-ordered kernels, so the
+    pipeline captures it inside its CUDA graphs: per step the host replays one graph, on every rank.  No NCCL kernel takes
+    SMs from the next batch's decode, no stream waits for a gather, nothing scales with the number of ranks on the host.
+
+    Control words (uint32, after the data regions of the symmetric buffer; every rank allocates the same layout):
+    ``flags[slot][r]`` at ``ctrl + 16*slot + r`` (used on dst), ``ack[slot]`` at ``ctrl + 32 + slot`` (used on writers).
+    """
+
+    kind = ("NMS kernel stores straight into rank 0's peer-mapped symmetric memory over NVLink and signals completion itself "
+            "(flag / acknowledge words; no extra launch on the writers, one 32-thread collect kernel per batch on rank 0, "
+            "all inside the step's CUDA graph)")
+    in_graph = True
+    MAX_WORLD = 16
 
     def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
         import torch.distributed._symmetric_memory as symm_mem
 
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), dst
+        if self.world > self.MAX_WORLD:
+            raise ValueError(f"PeerDelivery supports at most {self.MAX_WORLD} ranks")
         self.T, self.b_loc, self.max_det = T, b_loc, max_det
         self.n_d, self.n_c = T * b_loc * max_det * 6, T * b_loc
         self.n = (self.n_d + self.n_c + 63) // 64 * 64  # words per (slot, rank) region, 256-byte aligned
+        self.ctrl = 2 * self.world * self.n             # first control word
         try:
             symm_mem.enable_symm_mem_for_group(group.group_name)
         except Exception:
             pass  # newer builds enable it inside rendezvous()
-        self.local = symm_mem.empty(2 * self.world * self.n, dtype=torch.float32, device=device)
+        self.local = symm_mem.empty(self.ctrl + 64, dtype=torch.float32, device=device)
+        self.local[self.ctrl :].zero_()
         self.hdl = symm_mem.rendezvous(self.local, group)
         self.outs = []
         for slot in range(2):
@@ -176,42 +197,62 @@ class PeerDelivery:
                 region = self.hdl.get_buffer(dst, (self.n,), torch.float32, off)  # rank dst's memory, mapped here
             self.outs.append((region[: self.n_d].view(T, b_loc, max_det, 6),
                               region[self.n_d : self.n_d + self.n_c].view(torch.int32).view(T, b_loc)))
-        self.side = torch.cuda.Stream(device=device)
-        self.used = [False, False]
+        # local protocol state: seq[2], done[2] (writers), collected[2] (dst)
+        self.state = torch.zeros(8, dtype=torch.int32, device=device)
+        base = self.local.data_ptr() + 4 * self.ctrl
+        self._deliver = [None, None]
+        self._collect = [None, None]
+        self._peers = []  # keep the mapped views alive
+        for slot in range(2):
+            if self.rank != dst:
+                flag = self.hdl.get_buffer(dst, (1,), torch.float32, self.ctrl + 16 * slot + self.rank)
+                self._peers.append(flag)
+                self._deliver[slot] = (flag.data_ptr(), base + 4 * (32 + slot), self.state.data_ptr() + 4 * slot,
+                                       self.state.data_ptr() + 4 * (2 + slot))
+            else:
+                acks = []
+                for r in range(self.world):
+                    if r == dst:
+                        acks.append(None)
+                    else:
+                        a = self.hdl.get_buffer(r, (1,), torch.float32, self.ctrl + 32 + slot)
+                        self._peers.append(a)
+                        acks.append(a.data_ptr())
+                self._collect[slot] = (base + 4 * 16 * slot, acks, self.state.data_ptr() + 4 * (4 + slot))
+        torch.cuda.synchronize(device)
         self.hdl.barrier(channel=7)
 
+    def nms_deliver_args(self, slot: int):
+        """``deliver=`` argument of ``ops.nms_batched`` for the NMS launch that fills ``outs[slot]`` (None on dst: its own
+        rows are local and ordered by its stream)."""
+        return self._deliver[slot]
+
+    def collect(self, slot: int) -> None:
+        """dst: enqueue (current stream) the kernel that waits for every rank's batch in ``slot`` and acknowledges it.
+        A no-op on the other ranks."""
+        if self.rank != self.dst:
+            return
+        from . import _lib
+
+        flags, acks, collected = self._collect[slot]
+        dev = self.local.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().cerb_deliver_collect(flags, _lib.ptr_array(acks), collected, self.world, self.dst,
+                                                        torch.cuda.current_stream(dev).cuda_stream))
+
+    # the hand-shake lives in the kernels: nothing to do around a write
     def before_write(self, slot: int) -> None:
-        if self.rank != self.dst and self.used[slot]:
-            self.hdl.wait_signal(self.dst, channel=2 + slot)  # dst has taken the batch that was in this slot
+        pass
 
     def after_write(self, slot: int) -> None:
-        self.used[slot] = True
-        cur = torch.cuda.current_stream()
-        self.side.wait_stream(cur)  # the flag follows the kernel that filled the slot; the compute stream runs on
-        with torch.cuda.stream(self.side):
-            if self.rank != self.dst:
-                self.hdl.put_signal(self.dst, channel=slot)
-            else:
-                for r in range(self.world):
-                    if r != self.dst:
-                        self.hdl.wait_signal(r, channel=slot)      # rank r's batch has arrived
-                for r in range(self.world):
-                    if r != self.dst:
-                        self.hdl.put_signal(r, channel=2 + slot)   # ... and may be overwritten two batches from now
+        pass
 
     def drain(self) -> None:
-        torch.cuda.current_stream().wait_stream(self.side)
-        if self.rank != self.dst:  # consume outstanding acknowledgements so that the next run starts clean
-            for slot in range(2):
-                if self.used[slot]:
-                    self.hdl.wait_signal(self.dst, channel=2 + slot)
-                    self.used[slot] = False
-        else:
-            self.used = [False, False]
+        pass
 
     def result(self, slot: int):
-        """``(dets[T, world*B_loc, max_det, 6], counts[T, world*B_loc])`` on ``dst`` (after ``drain()`` and a device
-        synchronisation), ``(None, None)`` elsewhere."""
+        """``(dets[T, world*B_loc, max_det, 6], counts[T, world*B_loc])`` on ``dst`` (after the slot's ``collect`` has run
+        and the device was synchronised), ``(None, None)`` elsewhere."""
         if self.rank != self.dst:
             return None, None
         reg = self.local[slot * self.world * self.n : (slot + 1) * self.world * self.n].view(self.world, self.n)

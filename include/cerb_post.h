@@ -146,6 +146,30 @@ int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, 
                    size_t workspace_bytes, unsigned long long* stats, void* stream);
 
 /*
+ * Multi-GPU delivery without a collective (the one exchange of the path, the padded detections of every
+ * rank's images to rank dst).  cerb_nms_deliver is cerb_nms whose `dets` / `counts` point into a slot of rank dst's
+ * memory that is peer-mapped into this process (NVLink), plus four 32-bit words of protocol state:
+ *   flag_remote   in dst's memory (peer-mapped): the kernel's last CTA stores there, with release semantics at system
+ *                 scope and after every CTA has fenced its stores, the number of batches this rank has delivered into
+ *                 the slot;
+ *   ack_local     in this rank's memory, written remotely by dst (cerb_deliver_collect): batches dst has taken out of
+ *                 the slot.  Before its first store the kernel waits (bounded, ~2 s) until ack >= the batches it has
+ *                 written there, so a slot is never overwritten before dst has seen it;
+ *   seq_local, done_local   local counters owned by the kernel (zero-initialised once by the caller).
+ * cerb_deliver_collect is dst's side, a 32-thread kernel: for every rank r != dst wait until flags_local[r] exceeds
+ * *collected_local, then store the new count into ack_remote[r] (rank r's ack word, peer-mapped) and advance
+ * *collected_local.  Both are plain stream-ordered launches and can be captured in CUDA graphs; no NCCL kernel and no
+ * host synchronisation is on the data path.
+ */
+int cerb_nms_deliver(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
+                     double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
+                     int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace,
+                     size_t workspace_bytes, void* flag_remote, const void* ack_local, void* seq_local, void* done_local,
+                     void* stream);
+int cerb_deliver_collect(const void* flags_local, void* const* ack_remote, void* collected_local, int world, int dst,
+                         void* stream);
+
+/*
  * Decode + NMS for T task heads in one call (two launches on `stream`, no host work in between): the raw head
  * tensors go in, the padded detections come out; `y` (and `smax`, may be NULL) are caller-provided buffers that
  * receive the decoded predictions / score summary on the way (they are what Detect.forward would have returned).
@@ -227,7 +251,7 @@ int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_row
  * decode kernel instead of the pipelined one), "decode_order", "decode_vec", "decode_l2hint", "nms_minb" (1 | 2: the
  * 128- / 64-register NMS build), "nms_pdl" (0 = no programmatic dependent launch), "chunk_cap", "chunk_first",
  * "hist_sample", "ht_order" (head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = contiguous runs), "ht_stages"
- * (cap on its activation ring depth).
+ * (cap on its activation ring depth), "ht_groups" (its epilogue warp groups, 1 | 2).
  */
 int cerb_debug_set(const char* name, int value);
 int cerb_debug_reset(void);

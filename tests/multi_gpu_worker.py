@@ -50,10 +50,9 @@ def main():
     for prefer_peer in (True, False):
         deliv = make_delivery(len(ncs), len(mine), kw["max_det"], dev, prefer_peer=prefer_peer)
         kinds.append(type(deliv).__name__)
-        pipe = PostHeadPipeline(dev_heads, STRIDES, kw, outs=deliv.outs)
-        for rep in range(2):  # run the stream twice: the flags / buffers must be reusable
+        pipe = PostHeadPipeline(dev_heads, STRIDES, kw, outs=deliv.outs, delivery=deliv)
+        for rep, n_steps in enumerate((5, 4, 1, 2)):  # several runs: the flags / buffers must be reusable; 1 and 2 = the short-run graphs
             pipe.k, pipe.pending = 0, None
-            n_steps = 5
             for k in range(n_steps):
                 deliv.before_write((k - 1) & 1)
                 done = pipe.step()
