@@ -405,6 +405,8 @@ def main():
     # into rank 0's memory over NVLink (peer-mapped symmetric memory) or, failing that, into a packed local buffer that
     # one asynchronous NCCL gather moves.  Two buffers alternate with the pipeline's two output slots.
     delivery = make_delivery(len(NCS), B_PER_GPU, NMS_KW["max_det"], dev, prefer_peer=not args.serial) if world > 1 else None
+    if os.environ.get("CERB_DELIVERY") == "none":  # diagnostic only (tools/): N independent replicas, nothing reaches rank 0
+        delivery = None
     outs = delivery.outs if delivery is not None else None
 
     steps = args.steps
@@ -412,7 +414,7 @@ def main():
     n_timed = 0 if args.serial else min(TIMED_SLOTS if steps >= 128 else 16, max(steps - 1, 0))
     timed_at = sorted({1 + (i * (steps - 1)) // n_timed for i in range(n_timed)}) if n_timed else []
     pipe = PostHeadPipeline(heads_dev, STRIDES, NMS_KW, outs=outs, timed_parities=[k & 1 for k in timed_at], overlap=not args.serial,
-                            delivery=delivery)
+                            delivery=delivery, timed_steps=timed_at)
     slot_of = {k: i for i, k in enumerate(timed_at)}
 
     def run_steps(n, timed=False):
@@ -441,7 +443,7 @@ def main():
     last = (3 - 1) & 1
     assert torch.equal(pipe.outs[last][1], c_chk) and torch.equal(pipe.outs[last][0], d_chk), "pipeline != direct calls"
     equality = {"pipeline_equals_direct_calls": True}
-    if world > 1:
+    if world > 1 and delivery is not None and os.environ.get("CERB_SIDE", "branch") != "off":
         got = delivery.result(last)  # rank 0: (dets[T, world*B, max_det, 6], counts[T, world*B])
         for r in range(1, world):     # every shard's inputs travel to rank 0 once; rank 0 recomputes it alone
             shard = [[torch.empty_like(x) for x in lv] for lv in heads_dev] if rank == 0 else None
@@ -475,10 +477,13 @@ def main():
     elapsed_ms = t_start.elapsed_time(t_end)
     samples = [pipe.timed_ms(i) for i in range(len(timed_at))]
     nms_ms, dec_ms = [s[0] for s in samples], [s[1] for s in samples]
+    per_rank = None
     if world > 1:
-        tt = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tt.item())
+        mine = torch.tensor([elapsed_ms, sum(dec_ms) / max(len(dec_ms), 1), sum(nms_ms) / max(len(nms_ms), 1)], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 5) for v in t.tolist()] for t in allr]  # [elapsed ms, decode ms, NMS ms] of every rank
+        elapsed_ms = max(r[0] for r in per_rank)
 
     # ---- end to end through the host-buffer API (pinned host in, pinned host out)
     e2e_steps = max(3, min(args.steps, 10))
@@ -570,6 +575,9 @@ def main():
         line["launch_mode"] = "cuda_graphs, serial" if args.serial else "cuda_graphs, decode(k) overlapped with NMS(k-1) on two streams"
         line["clocks"] = clk.summary()
         line["equality"] = equality
+        if per_rank is not None:
+            line["per_rank_ms"] = {"elapsed": [r[0] for r in per_rank], "decode_instrumented": [r[1] for r in per_rank],
+                                   "nms_instrumented": [r[2] for r in per_rank]}
         if cfg5 is not None:
             line["config5_strong"] = cfg5
         if not args.no_extras and world == 1:

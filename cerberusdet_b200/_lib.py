@@ -26,6 +26,7 @@ EXPORTS = (
     "cerb_nms_stats",
     "cerb_nms_deliver",
     "cerb_deliver_collect",
+    "cerb_deliver_push",
     "cerb_decode_nms",
     "cerb_cross_task",
     "cerb_cross_task_workspace_bytes",
@@ -40,6 +41,15 @@ EXPORTS = (
 )
 
 _lib = None
+
+
+class Delivery(ctypes.Structure):
+    """``cerb_delivery`` of include/cerb_post.h."""
+
+    _fields_ = [("push_src", ctypes.c_void_p), ("push_dst", ctypes.c_void_p), ("push_words", ctypes.c_size_t),
+                ("flag_remote", ctypes.c_void_p), ("ack_local", ctypes.c_void_p), ("seq_local", ctypes.c_void_p),
+                ("done_local", ctypes.c_void_p), ("collect_flags", ctypes.c_void_p), ("collect_ack", ctypes.c_void_p * 16),
+                ("collect_count", ctypes.c_void_p), ("world", ctypes.c_int), ("dst", ctypes.c_int)]
 
 
 class CerbLibraryError(RuntimeError):
@@ -81,9 +91,11 @@ def load() -> ctypes.CDLL:
         lib.cerb_nms_stats.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp, vp]
     if hasattr(lib, "cerb_nms_deliver") or "CERB_LIB" not in os.environ:
         lib.cerb_nms_deliver.restype = i
-        lib.cerb_nms_deliver.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, vp, vp, vp, vp, vp]
+        lib.cerb_nms_deliver.argtypes = [vpp, ip, i, i, i, i, d, d, ip, i, i, i, i, i, d, vpp, vp, vp, vp, sz, ctypes.POINTER(Delivery), vp]
         lib.cerb_deliver_collect.restype = i
         lib.cerb_deliver_collect.argtypes = [vp, vpp, vp, i, i, vp]
+        lib.cerb_deliver_push.restype = i
+        lib.cerb_deliver_push.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp]
     lib.cerb_decode_nms.restype = i
     lib.cerb_decode_nms.argtypes = [vpp, ip, i, i, i, ip, ip, fp, i, vpp, vpp, d, d, ip, i, i, i, i, i, d, vp, vp, vp, sz, vp]
     lib.cerb_cross_task.restype = i

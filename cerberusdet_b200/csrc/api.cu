@@ -27,15 +27,18 @@ enum Knob {
     K_HT_ORDER,       // head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = one contiguous run of tiles per CTA
     K_HT_STAGES,      // head-tail kernel: cap on the activation ring depth (2..8)
     K_HT_GROUPS,      // head-tail kernel: epilogue groups (1 | 2)
+    K_PUSH_CTAS,      // delivery push kernel: CTAs (tools/side_probe.py)
+    K_PUSH_MODE,      // delivery push kernel: 0 = normal, 1 = no fences / flag (timing experiments only), 2 = no copy
     K_COUNT
 };
 static const char* const kKnobName[K_COUNT] = {"decode_pipe", "decode_order", "decode_vec", "decode_l2hint", "nms_minb",
                                                "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample",  "ht_order",
-                                               "ht_stages",   "ht_groups"};
+                                               "ht_stages",   "ht_groups",   "push_ctas",
+                                               "push_mode"};
 static const char* const kKnobEnv[K_COUNT] = {"CERB_DEBUG_DECODE_PIPE", "CERB_DEBUG_DECODE_ORDER", "CERB_DEBUG_DECODE_VEC",
                                               "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL",
                                               nullptr, nullptr, nullptr, "CERB_DEBUG_HT_ORDER", "CERB_DEBUG_HT_STAGES",
-                                              "CERB_DEBUG_HT_GROUPS"};
+                                              "CERB_DEBUG_HT_GROUPS", "CERB_DEBUG_PUSH_CTAS", "CERB_DEBUG_PUSH_MODE"};
 struct KnobTable {
     int v[K_COUNT];
     bool set[K_COUNT];
@@ -256,16 +259,10 @@ extern "C" int cerb_nms(const void* const* pred, const int* nc, int T, int B, in
                           max_nms, max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, stream);
 }
 
-struct NmsDelivery {
-    void* flag;
-    const void* ack;
-    void* seq;
-    void* done;
-};
 static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres, double iou_thres,
                     const int* classes, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, double max_wh,
                     const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes,
-                    unsigned long long* stats, const NmsDelivery* dv, void* stream);
+                    unsigned long long* stats, const cerb_delivery* dv, void* stream);
 
 extern "C" int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                               double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
@@ -278,14 +275,56 @@ extern "C" int cerb_nms_stats(const void* const* pred, const int* nc, int T, int
 extern "C" int cerb_nms_deliver(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                                 double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label,
                                 int max_det, int max_nms, double max_wh, const void* const* smax, float* dets, int* counts,
-                                void* workspace, size_t workspace_bytes, void* flag_remote, const void* ack_local,
-                                void* seq_local, void* done_local, void* stream) {
-    REQUIRE(flag_remote && ack_local && seq_local && done_local, "cerb_nms_deliver: null delivery pointer");
-    REQUIRE(aligned_to(flag_remote, 4) && aligned_to(ack_local, 4) && aligned_to(seq_local, 4) && aligned_to(done_local, 4),
-            "cerb_nms_deliver: delivery words must be 4-byte aligned");
-    const NmsDelivery dv = {flag_remote, ack_local, seq_local, done_local};
+                                void* workspace, size_t workspace_bytes, const cerb_delivery* dv, void* stream) {
+    REQUIRE(dv != nullptr, "cerb_nms_deliver: null delivery");
+    if (dv->flag_remote != nullptr) {
+        REQUIRE(dv->ack_local && dv->seq_local && dv->done_local, "cerb_nms_deliver: null protocol word");
+        REQUIRE(aligned_to(dv->flag_remote, 4) && aligned_to(dv->ack_local, 4) && aligned_to(dv->seq_local, 4) && aligned_to(dv->done_local, 4),
+                "cerb_nms_deliver: protocol words must be 4-byte aligned");
+    }
+    if (dv->push_src != nullptr) {
+        REQUIRE(dv->flag_remote != nullptr && dv->push_dst != nullptr, "cerb_nms_deliver: push_src needs push_dst and the protocol words");
+        REQUIRE(aligned_to(dv->push_src, 16) && aligned_to(dv->push_dst, 16) && dv->push_words % 4 == 0 && dv->push_words < (1ull << 32),
+                "cerb_nms_deliver: push buffers must be 16-byte aligned and hold a multiple of 4 words");
+    }
+    if (dv->collect_flags != nullptr) {
+        REQUIRE(dv->collect_count != nullptr && dv->world >= 1 && dv->world <= 16 && dv->dst >= 0 && dv->dst < dv->world,
+                "cerb_nms_deliver: bad collect side (world=%d dst=%d)", dv->world, dv->dst);
+        for (int r = 0; r < dv->world; ++r)
+            REQUIRE(r == dv->dst || dv->collect_ack[r] != nullptr, "cerb_nms_deliver: collect_ack[%d] is null", r);
+    }
     return nms_impl(pred, nc, T, B, A, dtype, conf_thres, iou_thres, classes, n_classes, agnostic, multi_label, max_det, max_nms,
-                    max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, &dv, stream);
+                    max_wh, smax, dets, counts, workspace, workspace_bytes, nullptr, dv, stream);
+}
+
+extern "C" int cerb_deliver_push(const void* src_local, void* dst_remote, size_t n_words, void* flag_remote, const void* ack_local,
+                                 void* seq_local, void* done_local, void* stream) {
+    g_err[0] = 0;
+    REQUIRE(src_local && dst_remote && flag_remote && ack_local && seq_local && done_local, "cerb_deliver_push: null argument");
+    REQUIRE(aligned_to(src_local, 16) && aligned_to(dst_remote, 16) && n_words % 4 == 0,
+            "cerb_deliver_push: buffers must be 16-byte aligned and hold a multiple of 4 words");
+    PushParams P;
+    P.src = (const float*)src_local;
+    P.dst = (float*)dst_remote;
+    P.n_words = n_words;
+    P.flag = (unsigned*)flag_remote;
+    P.ack = (const unsigned*)ack_local;
+    P.seq = (unsigned*)seq_local;
+    P.done = (unsigned*)done_local;
+    // 16 bytes per thread and sweep: enough CTAs to cover the batch in ~4 sweeps, at most 32 (it shares the GPU with the
+    // next batch's kernels)
+    size_t ctas = (n_words / 4 + 4 * 256 - 1) / (4 * 256);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 32) ctas = 32;
+    int kv = 0;
+    if (knob(K_PUSH_CTAS, &kv) && kv >= 1 && kv <= 1024) ctas = (size_t)kv;
+    P.mode = knob(K_PUSH_MODE, &kv) ? kv : 0;
+    cudaError_t e = cerb_launch_deliver_push(P, (int)ctas, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cerb_set_error("cerb_deliver_push: launch failed: %s", cudaGetErrorString(e));
+        return CERB_ECUDA;
+    }
+    return 0;
 }
 
 extern "C" int cerb_deliver_collect(const void* flags_local, void* const* ack_remote, void* collected_local, int world, int dst,
@@ -314,7 +353,7 @@ extern "C" int cerb_deliver_collect(const void* flags_local, void* const* ack_re
 static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres, double iou_thres,
                     const int* classes, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, double max_wh,
                     const void* const* smax, float* dets, int* counts, void* workspace, size_t workspace_bytes,
-                    unsigned long long* stats, const NmsDelivery* dv, void* stream) {
+                    unsigned long long* stats, const cerb_delivery* dv, void* stream) {
     g_err[0] = 0;
     REQUIRE(pred && nc, "cerb_nms: null argument");
     REQUIRE(T >= 1 && T <= CERB_MAX_TASKS, "cerb_nms: T=%d outside [1, %d]", T, CERB_MAX_TASKS);
@@ -365,10 +404,20 @@ static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A,
     P.counts = counts;
     P.pair_counts = stats;
     if (dv != nullptr) {
-        P.deliver_flag = (unsigned*)dv->flag;
-        P.deliver_ack = (const unsigned*)dv->ack;
-        P.deliver_seq = (unsigned*)dv->seq;
-        P.deliver_done = (unsigned*)dv->done;
+        P.deliver_flag = (unsigned*)dv->flag_remote;
+        P.deliver_ack = (const unsigned*)dv->ack_local;
+        P.deliver_seq = (unsigned*)dv->seq_local;
+        P.deliver_done = (unsigned*)dv->done_local;
+        P.push_src = (const float*)dv->push_src;
+        P.push_dst = (float*)dv->push_dst;
+        P.push_words = (unsigned)dv->push_words;
+        if (dv->collect_flags != nullptr) {
+            P.col_flags = (const unsigned*)dv->collect_flags;
+            for (int r = 0; r < dv->world; ++r) P.col_ack[r] = (unsigned*)dv->collect_ack[r];
+            P.col_collected = (unsigned*)dv->collect_count;
+            P.col_world = dv->world;
+            P.col_dst = dv->dst;
+        }
     }
     const size_t need = cerb_nms_kept_ws_bytes(T, B, max_det);
     if (need) {

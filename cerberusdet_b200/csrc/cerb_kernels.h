@@ -62,6 +62,17 @@ struct NmsParams {
     const unsigned* deliver_ack;   // local, written remotely by dst: batches dst has taken out of this slot
     unsigned* deliver_seq;         // local: batches this rank has written into this slot (kept by the kernel)
     unsigned* deliver_done;        // local: CTA completion counter of the running launch (zero between launches)
+    // piggyback form (default of shard.PeerDelivery): `dets` / `counts` are LOCAL; the launch additionally pushes the
+    // PREVIOUS batch's packed words (left in local staging by the previous launch) into dst's slot at its start -- the
+    // four words above then describe that slot -- so the remote stores have ~50 us to land before the fences at the end
+    const float* push_src;         // local staging of the previous batch (16-byte aligned), null = direct form
+    float* push_dst;               // dst's slot (peer-mapped)
+    unsigned push_words;           // multiple of 4
+    // rank dst: CTA 0 takes the batch the other ranks pushed during the previous step (cerb_deliver_collect's job)
+    const unsigned* col_flags;     // local [world], null = off
+    unsigned* col_ack[16];         // peer-mapped
+    unsigned* col_collected;       // local counter of that slot
+    int col_world, col_dst;
 };
 cudaError_t cerb_launch_nms(const NmsParams& P, int dtype, cudaStream_t stream);
 // dst's side of the delivery: one CTA; thread r waits until rank r's flag reaches (*collected + 1), then acknowledges
@@ -74,6 +85,17 @@ struct CollectParams {
     int world, dst;
 };
 cudaError_t cerb_launch_deliver_collect(const CollectParams& P, cudaStream_t stream);
+struct PushParams {
+    const float* src;      // local: one batch's packed words (dets rows, then counts), 16-byte aligned
+    float* dst;            // rank dst's slot (peer-mapped), 16-byte aligned
+    size_t n_words;        // 32-bit words to copy, a multiple of 4
+    unsigned* flag;        // dst's memory (peer-mapped)
+    const unsigned* ack;   // local, written remotely by dst
+    unsigned* seq;         // local
+    unsigned* done;        // local
+    int mode;              // 0; tools only: 1 = skip the fences and the flag, 2 = skip the copy
+};
+cudaError_t cerb_launch_deliver_push(const PushParams& P, int ctas, cudaStream_t stream);
 size_t cerb_nms_kept_ws_bytes(int T, int B, int max_det);
 
 // ------------------------------------------------------------------ cross-task merge

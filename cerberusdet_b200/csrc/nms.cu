@@ -688,6 +688,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -700,6 +705,32 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
     BLOCK_T_START
+    if (P.push_src != nullptr) {
+        // piggyback delivery: push the PREVIOUS batch (complete in local staging since the previous launch) into rank
+        // dst's slot before anything else; the fences that publish it are at the very end of this kernel, by when
+        // these stores have long landed.  dst must have taken the batch that was in the slot (never spins in steady
+        // state; bounded -- a lost peer must not hang the GPU).
+        if (threadIdx.x == 0) {
+            const unsigned need = *reinterpret_cast<volatile unsigned*>(P.deliver_seq);
+            for (unsigned spins = 0; ld_relaxed_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+        }
+        __syncthreads();
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(P.push_src);
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(P.push_dst);
+        for (unsigned i = blockIdx.x * NMS_THREADS + threadIdx.x; i < P.push_words / 4; i += gridDim.x * NMS_THREADS) dst4[i] = src[i];
+    }
+    if (P.col_flags != nullptr && blockIdx.x == 0) {
+        // rank dst: take the batch the other ranks pushed during the previous step and acknowledge it (one thread per rank)
+        const int r = threadIdx.x;
+        const unsigned need = *reinterpret_cast<volatile unsigned*>(P.col_collected) + 1u;
+        if (r < P.col_world && r != P.col_dst) {
+            for (unsigned spins = 0; ld_relaxed_sys(P.col_flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
+            (void)ld_acquire_sys(P.col_flags + r);
+            st_release_sys(P.col_ack[r], need);
+        }
+        __syncthreads();
+        if (r == 0) *reinterpret_cast<volatile unsigned*>(P.col_collected) = need;
+    }
     const int seg = blockIdx.x;
     const int task = seg / P.B, b = seg - task * P.B;
     const int nc = P.nc[task], A = P.A;
@@ -767,12 +798,15 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     // Programmatic dependent launch: this grid may have been started while the kernel before it in the stream (the
     // decode kernel) was still draining; nothing above touched global memory.  Wait for that kernel's results here.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (P.deliver_flag != nullptr && tid == 0) {
-        // the output slot lives in rank dst's memory: dst must have taken the batch this rank wrote there last time
-        // (two batches ago, so this never spins in steady state).  Bounded: a lost peer must not hang the GPU.
+    // direct delivery (cerb_nms_deliver): the output slot lives in rank dst's memory, and dst must have taken the batch this
+    // rank wrote there last time (two batches ago, so this never spins in steady state).  A relaxed load is enough: no
+    // data is read on the strength of it, it only gates stores (which are never speculated).  Bounded: a lost peer
+    // must not hang the GPU.
+    if (P.deliver_flag != nullptr && P.push_src == nullptr && tid == 0) {
         const unsigned need = *reinterpret_cast<volatile unsigned*>(P.deliver_seq);
-        for (unsigned spins = 0; ld_acquire_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
-    }  // (every path below passes a __syncthreads before the first store to dets)
+        for (unsigned spins = 0; ld_relaxed_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+    }
+    // (every path below passes a __syncthreads before the first store to dets)
     if (smax) build_hist_summary(); else build_hist(hstride, NMS_BINS);
     PROF(1);  // first histogram
 
@@ -1121,17 +1155,20 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     // rows past the count are zero so the padded [T, B, max_det, 6] output is deterministic without a separate fill
     for (int i = kept * 6 + tid; i < max_det * 6; i += NMS_THREADS) dets[i] = 0.f;
     if (P.deliver_flag != nullptr) {
-        // tell rank dst that this rank's batch is complete: every CTA publishes its (remote) stores system-wide and
-        // counts itself; the last one bumps the slot's sequence number and releases it into dst's flag
+        // tell rank dst that this rank's batch is complete.  Every CTA orders its stores before its count at GPU scope
+        // (fence + atomic = release; the per-CTA fence is the cheap one); the last CTA -- which has observed every count
+        // (acquire at GPU scope) -- fences ONCE at system scope and releases the slot's new sequence number into dst's
+        // flag.  PTX causality order is transitive across the two scopes, so a reader on dst that acquires the flag sees
+        // every CTA's rows.
         __syncthreads();
         if (tid == 0) {
-            __threadfence_system();
+            __threadfence();
             if (atomicAdd(P.deliver_done, 1u) == gridDim.x - 1) {
+                __threadfence();
                 *reinterpret_cast<volatile unsigned*>(P.deliver_done) = 0u;
                 const unsigned n = *reinterpret_cast<volatile unsigned*>(P.deliver_seq) + 1u;
                 *reinterpret_cast<volatile unsigned*>(P.deliver_seq) = n;
-                __threadfence_system();
-                st_release_sys(P.deliver_flag, n);
+                st_release_sys(P.deliver_flag, n);  // (release = system-scope fence + store)
             }
         }
     }
@@ -1145,12 +1182,50 @@ __global__ void deliver_collect_kernel(const __grid_constant__ CollectParams P) 
     const int r = threadIdx.x;
     const unsigned need = *reinterpret_cast<volatile unsigned*>(P.collected) + 1u;
     if (r < P.world && r != P.dst) {
-        for (unsigned spins = 0; ld_acquire_sys(P.flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
+        // poll with relaxed loads (an acquire load is a load plus a system-scope fence: not something to repeat every
+        // 256 ns beside a memory-bound kernel), then acquire once
+        for (unsigned spins = 0; ld_relaxed_sys(P.flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
+        (void)ld_acquire_sys(P.flags + r);
         st_release_sys(P.ack[r], need);
     }
     __syncthreads();
     if (r == 0) *reinterpret_cast<volatile unsigned*>(P.collected) = need;
 }
+// a writer's side of the peer delivery, off the critical path: the NMS kernel left the padded rows of one batch in LOCAL
+// memory; this small kernel pushes them into rank dst's slot over NVLink (128-bit stores) and runs the hand-shake -- wait
+// for dst's acknowledgement of the batch that was in the slot, copy, order the stores (GPU-scope release per CTA, one
+// system-scope release by the last CTA) and publish the slot's new sequence number in dst's flag word.  The fences'
+// NVLink round trips cost this kernel a few microseconds and nobody else anything: it runs beside the next batch's
+// decode / NMS kernels.
+__global__ void __launch_bounds__(256) deliver_push_kernel(const __grid_constant__ PushParams P) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const unsigned need = *reinterpret_cast<volatile unsigned*>(P.seq);
+        for (unsigned spins = 0; ld_relaxed_sys(P.ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+    }
+    __syncthreads();
+    const size_t n4 = P.n_words / 4;
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(P.src);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(P.dst);
+    if (P.mode != 2)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (tid == 0 && P.mode != 1) {
+        __threadfence();
+        if (atomicAdd(P.done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(P.done) = 0u;
+            const unsigned n = *reinterpret_cast<volatile unsigned*>(P.seq) + 1u;
+            *reinterpret_cast<volatile unsigned*>(P.seq) = n;
+            st_release_sys(P.flag, n);
+        }
+    }
+}
+cudaError_t cerb_launch_deliver_push(const PushParams& P, int ctas, cudaStream_t stream) {
+    deliver_push_kernel<<<ctas, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t cerb_launch_deliver_collect(const CollectParams& P, cudaStream_t stream) {
     deliver_collect_kernel<<<1, 32, 0, stream>>>(P);
     return cudaGetLastError();

@@ -185,10 +185,10 @@ def _nms_impl(
     smax: Sequence[torch.Tensor],
     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     stats: Optional[torch.Tensor] = None,
-    deliver: Optional[Tuple[int, int, int, int]] = None,
+    deliver=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``deliver`` = device addresses ``(flag_remote, ack_local, seq_local, done_local)`` of the multi-GPU delivery
-    protocol (``cerb_nms_deliver``; shard.PeerDelivery owns the words), ``out`` then lives in rank dst's memory."""
+    """``deliver`` = a ``_lib.Delivery`` (``cerb_delivery``, include/cerb_post.h) built by ``shard.PeerDelivery``: this
+    launch's part in the multi-GPU delivery (``cerb_nms_deliver``)."""
     lib = _lib.load()
     T = len(preds)
     first = preds[0]
@@ -233,7 +233,7 @@ def _nms_impl(
         if deliver is not None:
             if stats is not None or out is None:
                 raise ValueError("deliver= needs out= (the peer-mapped slot) and excludes stats=")
-            rc = lib.cerb_nms_deliver(*head, *[int(a) for a in deliver], _stream_ptr(dev))
+            rc = lib.cerb_nms_deliver(*head, ctypes.byref(deliver), _stream_ptr(dev))
         else:
             rc = lib.cerb_nms_stats(*head, stats.data_ptr() if stats is not None else None, _stream_ptr(dev))
     _lib.check(rc)
@@ -501,7 +501,7 @@ def nms_batched(
     max_wh: float = MAX_WH,
     use_summary: bool = True,
     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-    deliver: Optional[Tuple[int, int, int, int]] = None,
+    deliver=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """All task heads, all images, one launch.  Returns padded ``dets[T,B,max_det,6]`` and
     ``counts[T,B]`` (device tensors; no host sync).  Predictions that came out of ``decode_heads``
@@ -518,7 +518,7 @@ def nms_batched(
             smax = found
     args = (preds, float(conf_thres), float(iou_thres), None if classes is None else [int(c) for c in classes],
             bool(agnostic), bool(multi_label), int(max_det), int(max_nms), float(max_wh), smax)
-    if deliver is not None:  # multi-GPU: out is a slot in rank dst's memory, the kernel runs the delivery protocol itself
+    if deliver is not None:  # multi-GPU: the launch also runs this rank's part of the delivery to rank dst
         return _nms_impl(*args, out=out, deliver=deliver)
     if out is not None:
         nms_out_op(*args, out[0], out[1])

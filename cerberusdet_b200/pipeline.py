@@ -15,6 +15,7 @@ which may be caller-provided (e.g. ``shard.DetectionGatherer`` buffers, or rank 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -22,19 +23,24 @@ import torch
 from . import ops
 
 
+# tools/ A/B only: "piggyback" (default) = the delivery rides on the NMS launches; "branch3" = stand-alone delivery kernels
+# on a third branch of the step graph; "after" = small graphs replayed after the step graph; "off" = never (nothing is
+# delivered: timing experiments only)
+_SIDE = os.environ.get("CERB_SIDE", "piggyback")
+
+
 class PostHeadPipeline:
     def __init__(self, heads: Sequence[Sequence[torch.Tensor]], strides: Sequence[float], nms_kw: dict,
                  outs: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None, timed_parities: Sequence[int] = (),
-                 overlap: bool = True, delivery=None):
+                 overlap: bool = True, delivery=None, timed_steps: Sequence[int] = ()):
         """``heads[t][l]``: static raw head tensors ``[B, 64+nc_t, H_l, W_l]`` on one CUDA device.  ``outs``: two
         ``(dets[T,B,max_det,6] float32, counts[T,B] int32)`` buffer pairs (allocated here when omitted).
         ``timed_parities`` additionally captures one instrumented step graph per entry (the NMS kernel, then the decode
         kernel alone, each between timing events recorded by the graph itself) for ``step(timed=i)``; entry i is the
         parity (step index & 1) of the step slot i will be used at.  ``overlap=False`` captures the serial
         order (decode -> NMS of the same batch, one stream) behind the same interface.
-        ``delivery`` (N > 1): a ``shard.PeerDelivery`` whose hand-shake runs inside the kernels (``in_graph``): the NMS
-        launches carry its protocol words and rank dst's ``collect`` of the batch delivered one step earlier is captured
-        in the same step graph, so a step stays ONE graph replay on every rank."""
+        ``delivery`` (N > 1): a ``shard.PeerDelivery`` (``in_graph``): its push / collect kernels are captured on a side
+        branch of the step graphs (see ``_capture``), so a step stays ONE graph replay on every rank."""
         first = heads[0][0]
         if not first.is_cuda:
             raise TypeError("PostHeadPipeline needs CUDA tensors (cerberusdet_b200 has no CPU path)")
@@ -59,54 +65,67 @@ class PostHeadPipeline:
         self.pending = None   # parity of the decoded batch whose NMS has not been issued yet
         with torch.cuda.device(self.device):
             self.ybuf = [ops.decode_buffers(self.heads) for _ in range(2)]
-            self.sa, self.sb = torch.cuda.Stream(), torch.cuda.Stream()
+            self.sa, self.sb, self.sc = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
             # eager warm-up of both kernels (module load, function attributes) before anything is captured
             ys = ops.decode_heads(self.heads, self.strides, out=self.ybuf[0])
             ops.nms_batched(ys, out=self.outs[0], **self.kw)
             torch.cuda.synchronize(self.device)
             self._g_first = [self._capture(p, nms_of=None) for p in (0, 1)]              # decode only (first step)
-            self._g_step = [self._capture(p, nms_of=p if not self.overlap else 1 - p, collect=True) for p in (0, 1)]
-            self._g_flush = [self._capture(None, nms_of=p, collect=True) for p in (0, 1)]              # NMS only (drain)
+            self._g_step = [self._capture(p, nms_of=p if not self.overlap else 1 - p) for p in (0, 1)]
+            self._g_flush = [self._capture(None, nms_of=p) for p in (0, 1)]              # NMS only (drain)
             if self.delivery is not None:
-                # second step of a run: nothing has been delivered into the other slot yet, so nothing to collect;
-                # a run of one step: only the flushed batch is collected; after an instrumented step: collect alone
-                self._g_step1 = self._capture(1, nms_of=0, collect=False)
-                self._g_flush1 = self._capture(None, nms_of=0, collect="own")
-                self._g_collect = [self._capture_collect(p) for p in (0, 1)]
+                # steady state (step k >= 3): the step graph also carries, on a third branch, this rank's side of the
+                # delivery -- writers push batch k-2, rank dst collects batch k-3; the first steps of a run, instrumented
+                # steps and the flush use the plain graphs above plus these two small ones
+                self._g_full = [self._capture(p, nms_of=1 - p, side=True) for p in (0, 1)]
+                self._g_flush_full = [self._capture(None, nms_of=p, side=True) for p in (0, 1)]
+                self._g_push = [self._capture_side(p, "push") for p in (0, 1)]
+                self._g_collect = [self._capture_side(p, "collect") for p in (0, 1)]
             self.timed: List[Tuple[torch.cuda.CUDAGraph, list]] = []
+            # ``timed_steps`` (optional, same length): the step index each instrumented slot is used at; with a delivery,
+            # slots used at steps >= 3 carry the side branch like the steady-state graph does
             self.timed_parity = [int(p) & 1 for p in timed_parities]
-            for p in self.timed_parity:
-                self.timed.append(self._capture_timed(p))
+            self.timed_has_side = [self.delivery is not None and _SIDE == "piggyback" and i < len(timed_steps) and int(timed_steps[i]) >= 3
+                                   for i in range(len(self.timed_parity))]
+            for p, side in zip(self.timed_parity, self.timed_has_side):
+                self.timed.append(self._capture_timed(p, side))
             torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ graph construction
     def _decode(self, p):
         return ops.decode_heads(self.heads, self.strides, out=self.ybuf[p])
 
-    def _nms(self, p):
+    def _nms(self, p, piggyback: bool = False):
         T = len(self.heads)
         ys = self.ybuf[p][:T]
         for y, sm in zip(ys, self.ybuf[p][T:]):  # the summary of a static buffer describes whatever decode wrote last
             if sm.shape[-1]:
                 ops._remember_summary(y, sm)
-        deliver = self.delivery.nms_deliver_args(p) if self.delivery is not None else None
+        deliver = self.delivery.nms_deliver_args(p, piggyback) if self.delivery is not None else None
         return ops.nms_batched(ys, out=self.outs[p], deliver=deliver, **self.kw)
 
-    def _capture_collect(self, slot: int):
-        if self.delivery.rank != self.delivery.dst:
-            return None  # collect() is dst's side only
+    def _capture_side(self, slot: int, what: str):
+        """A graph holding only this rank's delivery kernel for ``slot`` (None where that side does not exist here)."""
+        dv = self.delivery
+        on_dst = dv.rank == dv.dst
+        if (what == "collect") != on_dst or (what == "push" and dv.direct):
+            return None
         g = torch.cuda.CUDAGraph()
         self.sa.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.sa):
             with torch.cuda.graph(g, stream=self.sa):
-                self.delivery.collect(slot)
+                dv.collect(slot) if on_dst else dv.push(slot)
         torch.cuda.current_stream(self.device).wait_stream(self.sa)
         return g
 
-    def _capture(self, dec: Optional[int], nms_of: Optional[int], collect=False):
-        """``collect`` (in-graph delivery, rank dst): True = after the NMS also collect the batch delivered one step
-        earlier (the other slot), and for a flush both; "own" = only the batch this NMS delivers."""
+    def _capture(self, dec: Optional[int], nms_of: Optional[int], side: bool = False):
+        """``side`` (in-graph delivery, steady state): the NMS launch also carries this rank's side of the delivery of an
+        earlier batch (``PeerDelivery.nms_deliver_args(slot, piggyback=True)``): a writer's launch for batch j pushes
+        batch j-1, rank dst's launch for batch j takes batch j-2.  CERB_SIDE=branch (tools/ A/B) puts the stand-alone
+        kernels on a third branch instead."""
         dv = self.delivery
+        branch = side and _SIDE == "branch3" and (dv.rank == dv.dst or not dv.direct)
+        piggy = side and not branch
         g = torch.cuda.CUDAGraph()
         self.sa.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.sa):
@@ -114,27 +133,30 @@ class PostHeadPipeline:
                 if self.overlap or dec is None or nms_of is None:
                     if nms_of is not None and dec is not None:
                         self.sb.wait_stream(self.sa)
+                        if branch:
+                            self.sc.wait_stream(self.sa)
+                            with torch.cuda.stream(self.sc):
+                                if dv.rank == dv.dst:
+                                    dv.collect(1 - dec)
+                                else:
+                                    dv.push(dec)
                         with torch.cuda.stream(self.sb):
-                            self._nms(nms_of)
-                            if dv is not None and collect:
-                                dv.collect(1 - nms_of)  # the batch the other ranks delivered during the previous step
+                            self._nms(nms_of, piggy)
                         self._decode(dec)
                         self.sa.wait_stream(self.sb)
+                        if branch:
+                            self.sa.wait_stream(self.sc)
                     elif dec is not None:
                         self._decode(dec)
                     else:
-                        self._nms(nms_of)
-                        if dv is not None and collect is True:
-                            dv.collect(1 - nms_of)
-                        if dv is not None and collect:
-                            dv.collect(nms_of)
+                        self._nms(nms_of, piggy)
                 else:  # serial: decode -> NMS of the SAME batch (the NMS kernel starts under programmatic dependent launch)
                     self._decode(dec)
                     self._nms(nms_of)
         torch.cuda.current_stream(self.device).wait_stream(self.sa)
         return g
 
-    def _capture_timed(self, p: int):
+    def _capture_timed(self, p: int, side: bool = False):
         """Instrumented step: the same two launches as a normal step (decode of this batch, NMS of the previous one) in
         SERIAL order with timing events recorded by graph nodes:  E0 ; decode ; {E1 on a side branch} ; NMS ; E2.
         E1 hangs off the decode kernel on a second stream, so the NMS kernel keeps its programmatic (early-launch) edge
@@ -148,13 +170,28 @@ class PostHeadPipeline:
                 self._decode(p)
                 self.sb.wait_stream(self.sa)
                 ev[1].record(self.sb)
-                self._nms(1 - p)
+                self._nms(1 - p, side)  # (side: the launch carries this rank's delivery work, as in the steady-state graph)
                 ev[2].record(self.sa)
                 self.sa.wait_stream(self.sb)
         torch.cuda.current_stream(self.device).wait_stream(self.sa)
         return g, ev
 
     # ------------------------------------------------------------------ running
+    def _deliver_side(self, k: int) -> None:
+        """This rank's delivery work that belongs to step ``k`` -- push batch k-2 (writers), collect batch k-3 (dst) -- as
+        stand-alone kernels (the first steps of a run, instrumented steps without the piggyback, CERB_SIDE=after)."""
+        dv = self.delivery
+        if _SIDE == "off":
+            return
+        if dv.rank == dv.dst:
+            if k >= 3:
+                self._g_collect[(k - 3) & 1].replay()
+                self._collected = k - 2
+        elif k >= 2:
+            if self._g_push[0] is not None:
+                self._g_push[(k - 2) & 1].replay()
+            self._pushed = k - 1
+
     def step(self, timed: Optional[int] = None) -> Optional[int]:
         """Issue one pipeline step on the current stream.  Returns the index of the ``outs`` buffer that this step's
         NMS fills (the detections of the PREVIOUS batch; of this batch when ``overlap=False``), or None on the first
@@ -168,30 +205,50 @@ class PostHeadPipeline:
         if self.pending is None:
             self._g_first[p].replay()
             self.pending = p
+            self._pushed = self._collected = 0  # batches of this run already pushed (writer) / collected (dst)
             return None
+        in_launch = self.delivery is not None and k >= 3 and _SIDE in ("piggyback", "branch3")
         if timed is not None:
             g, _ = self.timed[timed]
             if self.timed_parity[timed] != p:
                 raise ValueError("timed slot parity does not match the step parity")
             g.replay()
-            if self.delivery is not None and k >= 2 and self._g_collect[p] is not None:
-                self._g_collect[p].replay()  # (the instrumented graph holds the two kernels and their events only)
-        elif self.delivery is not None and k < 2:
-            self._g_step1.replay()           # second step of a run: no batch in the other slot yet
+            in_launch = in_launch and self.timed_has_side[timed]
+        elif in_launch:
+            self._g_full[p].replay()
         else:
             self._g_step[p].replay()
+        if self.delivery is not None:
+            if in_launch:  # the step's launches did it: push k-2 / collect k-3
+                self._pushed, self._collected = k - 1, k - 2
+            else:
+                self._deliver_side(k)
         done, self.pending = self.pending, p
         return done
 
     def flush(self) -> Optional[int]:
-        """NMS of the last decoded batch (end of a stream of batches).  Returns its ``outs`` index."""
+        """NMS of the last decoded batch (end of a stream of batches), and -- with a delivery -- everything of this run that
+        is still on its way to rank dst.  Returns the ``outs`` index of the last batch."""
         if not self.overlap or self.pending is None:
             return None
         p, self.pending = self.pending, None
-        if self.delivery is not None and self.k < 2:
-            self._g_flush1.replay()  # a run of one step: only the flushed batch is there to collect
+        n = self.k  # steps of this run = batches 0 .. n-1
+        dv = self.delivery
+        if dv is not None and n >= 3 and _SIDE == "piggyback":
+            self._g_flush_full[p].replay()  # the last NMS launch carries push n-2 / collect n-3 like every other one
+            self._pushed, self._collected = n - 1, n - 2
         else:
             self._g_flush[p].replay()
+        if dv is not None and _SIDE != "off":
+            if dv.rank == dv.dst:
+                for j in range(self._collected, n):
+                    self._g_collect[j & 1].replay()
+                self._collected = n
+            else:
+                for j in range(self._pushed, n):
+                    if self._g_push[0] is not None:
+                        self._g_push[j & 1].replay()
+                self._pushed = n
         return p
 
     def timed_ms(self, i: int) -> Tuple[float, float]:

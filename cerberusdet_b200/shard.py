@@ -9,6 +9,7 @@ GPUs; gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -145,38 +146,54 @@ class GatherDelivery:
     def collect(self, slot: int) -> None:
         pass
 
+    def push(self, slot: int) -> None:
+        pass
+
 
 class PeerDelivery:
-    """Per-batch delivery WITHOUT a collective and without a single extra launch on the writers: every rank's NMS kernel
-    writes its padded detections straight into rank ``dst``'s memory over NVLink -- ``outs[slot]`` on rank r are views of
-    rank dst's symmetric-memory buffer (``torch.distributed._symmetric_memory``: peer-mapped device memory), region
-    (slot, r) -- and runs the hand-shake itself (``cerb_nms_deliver``, include/cerb_post.h):
+    """Per-batch delivery WITHOUT a collective: every rank pushes the padded detections of its batch straight into rank
+    ``dst``'s memory over NVLink (``torch.distributed._symmetric_memory``: peer-mapped device memory, region (slot, r) of
+    dst's buffer) and the hand-shake is a pair of 32-bit words per slot, moved by the kernels themselves:
 
-      * its last CTA, after every CTA has fenced its remote stores, releases the slot's batch count into dst's flag word;
-      * before its first store it checks that dst has acknowledged the batch it wrote into this slot two batches ago.
+      * writer r: ``push(slot)`` = ``cerb_deliver_push`` -- a small kernel that waits until dst has acknowledged the batch
+        that was in the slot, copies the packed rows with 128-bit stores, orders them (GPU-scope release per CTA, one
+        system-scope release by the last CTA) and publishes the slot's batch count in dst's ``flags[slot][r]``;
+      * dst: ``collect(slot)`` = ``cerb_deliver_collect`` -- one 32-thread kernel: thread r waits for rank r's flag and
+        stores the acknowledgement into rank r's ``ack[slot]``.
 
-    Rank ``dst`` runs one 32-thread kernel per batch (``collect(slot)`` -> ``cerb_deliver_collect``): thread r waits for
-    rank r's flag and stores the acknowledgement into rank r's memory.  All of it is stream-ordered kernels, so the
-    pipeline captures it inside its CUDA graphs: per step the host replays one graph, on every rank.  No NCCL kernel takes
-    SMs from the next batch's decode, no stream waits for a gather, nothing scales with the number of ranks on the host.
+    The NMS kernel writes LOCAL memory exactly as on one GPU.  In steady state neither side is a kernel of its own: the
+    NEXT NMS launch carries them (``nms_deliver_args(slot, piggyback=True)`` -> ``cerb_nms_deliver``): a writer's launch
+    pushes the previous batch at its start and publishes the flag at its end, ~50 us later, when the stores have long
+    landed; CTA 0 of dst's launch does the collect.  The step graph keeps the shape it has on one GPU (a third graph
+    branch, however small its kernel, costs the decode / NMS overlap: +13 us per step, profiles/r02_multi_gpu.md), the
+    NVLink round trips of the fences are on nobody's critical path, and a step stays one graph replay on every rank.
+    ``push`` / ``collect`` as stand-alone kernels serve the first and last batches of a run.  No NCCL kernel takes SMs
+    from the decode, no stream waits for a gather, nothing on the host scales with the number of ranks.
+
+    ``direct=True`` is the variant without the staging copy: ``outs[slot]`` ARE dst's memory and the NMS kernel runs the
+    writer's side of the hand-shake itself (``cerb_nms_deliver``); its fences then sit at the end of the NMS kernel
+    (+7 us per step at N=2, profiles/r02_multi_gpu.md), so it is not the default.
 
     Control words (uint32, after the data regions of the symmetric buffer; every rank allocates the same layout):
     ``flags[slot][r]`` at ``ctrl + 16*slot + r`` (used on dst), ``ack[slot]`` at ``ctrl + 32 + slot`` (used on writers).
     """
 
-    kind = ("NMS kernel stores straight into rank 0's peer-mapped symmetric memory over NVLink and signals completion itself "
-            "(flag / acknowledge words; no extra launch on the writers, one 32-thread collect kernel per batch on rank 0, "
-            "all inside the step's CUDA graph)")
     in_graph = True
     MAX_WORLD = 16
 
-    def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None):
+    def __init__(self, T: int, b_loc: int, max_det: int, device, dst: int = 0, group=None, direct: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
 
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), dst
         if self.world > self.MAX_WORLD:
             raise ValueError(f"PeerDelivery supports at most {self.MAX_WORLD} ranks")
+        self.direct = bool(direct)
+        self.kind = ("rows pushed into rank 0's peer-mapped symmetric memory over NVLink by " +
+                     ("the NMS kernel as it produces them (cerb_nms_deliver, direct form)" if self.direct else
+                      "the NEXT NMS launch at its start (cerb_nms_deliver, piggyback form: staged locally, 128-bit stores)") +
+                     "; flag / acknowledge words instead of a collective, published / taken by the same launches; "
+                     "no extra node in the step graphs")
         self.T, self.b_loc, self.max_det = T, b_loc, max_det
         self.n_d, self.n_c = T * b_loc * max_det * 6, T * b_loc
         self.n = (self.n_d + self.n_c + 63) // 64 * 64  # words per (slot, rank) region, 256-byte aligned
@@ -188,27 +205,31 @@ class PeerDelivery:
         self.local = symm_mem.empty(self.ctrl + 64, dtype=torch.float32, device=device)
         self.local[self.ctrl :].zero_()
         self.hdl = symm_mem.rendezvous(self.local, group)
-        self.outs = []
-        for slot in range(2):
-            off = (slot * self.world + self.rank) * self.n
-            if self.rank == dst:
-                region = self.local[off : off + self.n]
-            else:
-                region = self.hdl.get_buffer(dst, (self.n,), torch.float32, off)  # rank dst's memory, mapped here
-            self.outs.append((region[: self.n_d].view(T, b_loc, max_det, 6),
-                              region[self.n_d : self.n_d + self.n_c].view(torch.int32).view(T, b_loc)))
+        on_dst = self.rank == dst
         # local protocol state: seq[2], done[2] (writers), collected[2] (dst)
         self.state = torch.zeros(8, dtype=torch.int32, device=device)
         base = self.local.data_ptr() + 4 * self.ctrl
-        self._deliver = [None, None]
-        self._collect = [None, None]
-        self._peers = []  # keep the mapped views alive
+        self.outs, self._remote, self._stage = [], [None, None], [None, None]
+        self._words = [None, None]    # writers: (flag_remote, ack_local, seq_local, done_local) per slot
+        self._collect = [None, None]  # dst: (flags_local, [ack_remote per rank], collected_local) per slot
+        self._peers = []              # keep the mapped views alive
         for slot in range(2):
-            if self.rank != dst:
+            off = (slot * self.world + self.rank) * self.n
+            if on_dst:
+                region = self.local[off : off + self.n]
+            else:
+                self._remote[slot] = self.hdl.get_buffer(dst, (self.n,), torch.float32, off)  # rank dst's memory, mapped here
+                if self.direct:
+                    region = self._remote[slot]
+                else:
+                    region = self._stage[slot] = torch.zeros(self.n, dtype=torch.float32, device=device)
+            self.outs.append((region[: self.n_d].view(T, b_loc, max_det, 6),
+                              region[self.n_d : self.n_d + self.n_c].view(torch.int32).view(T, b_loc)))
+            if not on_dst:
                 flag = self.hdl.get_buffer(dst, (1,), torch.float32, self.ctrl + 16 * slot + self.rank)
                 self._peers.append(flag)
-                self._deliver[slot] = (flag.data_ptr(), base + 4 * (32 + slot), self.state.data_ptr() + 4 * slot,
-                                       self.state.data_ptr() + 4 * (2 + slot))
+                self._words[slot] = (flag.data_ptr(), base + 4 * (32 + slot), self.state.data_ptr() + 4 * slot,
+                                     self.state.data_ptr() + 4 * (2 + slot))
             else:
                 acks = []
                 for r in range(self.world):
@@ -222,10 +243,52 @@ class PeerDelivery:
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=7)
 
-    def nms_deliver_args(self, slot: int):
-        """``deliver=`` argument of ``ops.nms_batched`` for the NMS launch that fills ``outs[slot]`` (None on dst: its own
-        rows are local and ordered by its stream)."""
-        return self._deliver[slot]
+    def nms_deliver_args(self, slot: int, piggyback: bool = False):
+        """``deliver=`` argument (a ``_lib.Delivery`` or None) of ``ops.nms_batched`` for the NMS launch that fills
+        ``outs[slot]``.  ``piggyback``: the launch also does this rank's side of the delivery of an EARLIER batch -- a
+        writer pushes the batch it left in the other slot's staging by its previous launch, rank dst takes the batch the
+        writers pushed into this slot's parity during the previous step (see ``PostHeadPipeline``).  ``direct`` mode: a
+        writer's launch stores into dst's memory and signals for its own batch."""
+        from . import _lib
+
+        on_dst = self.rank == self.dst
+        if self.direct:
+            if on_dst:
+                return self._collect_struct(slot) if piggyback else None
+            d = _lib.Delivery()
+            d.flag_remote, d.ack_local, d.seq_local, d.done_local = self._words[slot]
+            return d
+        if not piggyback:
+            return None
+        if on_dst:
+            return self._collect_struct(slot)
+        prev = 1 - slot
+        d = _lib.Delivery()
+        d.push_src, d.push_dst, d.push_words = self._stage[prev].data_ptr(), self._remote[prev].data_ptr(), self.n
+        d.flag_remote, d.ack_local, d.seq_local, d.done_local = self._words[prev]
+        return d
+
+    def _collect_struct(self, slot: int):
+        from . import _lib
+
+        flags, acks, collected = self._collect[slot]
+        d = _lib.Delivery()
+        d.collect_flags, d.collect_count, d.world, d.dst = flags, collected, self.world, self.dst
+        for r, a in enumerate(acks):
+            d.collect_ack[r] = a
+        return d
+
+    def push(self, slot: int) -> None:
+        """Writer: enqueue (current stream) the kernel that moves the batch in ``outs[slot]`` into dst's slot and signals
+        it.  A no-op on dst and in ``direct`` mode."""
+        if self.rank == self.dst or self.direct:
+            return
+        from . import _lib
+
+        dev = self.local.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().cerb_deliver_push(self._stage[slot].data_ptr(), self._remote[slot].data_ptr(), self.n,
+                                                     *self._words[slot], torch.cuda.current_stream(dev).cuda_stream))
 
     def collect(self, slot: int) -> None:
         """dst: enqueue (current stream) the kernel that waits for every rank's batch in ``slot`` and acknowledges it.
@@ -240,7 +303,7 @@ class PeerDelivery:
             _lib.check(_lib.load().cerb_deliver_collect(flags, _lib.ptr_array(acks), collected, self.world, self.dst,
                                                         torch.cuda.current_stream(dev).cuda_stream))
 
-    # the hand-shake lives in the kernels: nothing to do around a write
+    # the hand-shake lives in kernels the pipeline enqueues: nothing to do around a write
     def before_write(self, slot: int) -> None:
         pass
 
@@ -267,11 +330,12 @@ def make_delivery(T: int, b_loc: int, max_det: int, device, dst: int = 0, group=
     (all ranks agree, so nobody is left in a collective alone), else the gather."""
     import os
 
-    want_peer = prefer_peer and torch.device(device).type == "cuda" and os.environ.get("CERB_DELIVERY", "peer") != "gather"
+    mode = os.environ.get("CERB_DELIVERY", "peer")
+    want_peer = prefer_peer and torch.device(device).type == "cuda" and mode != "gather"
     if want_peer:
         ok, deliv = 1, None
         try:
-            deliv = PeerDelivery(T, b_loc, max_det, device, dst=dst, group=group)
+            deliv = PeerDelivery(T, b_loc, max_det, device, dst=dst, group=group, direct=(mode == "peer_direct"))
         except Exception as exc:  # pragma: no cover - depends on the box / torch build
             import sys
 

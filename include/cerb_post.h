@@ -146,26 +146,51 @@ int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, 
                    size_t workspace_bytes, unsigned long long* stats, void* stream);
 
 /*
- * Multi-GPU delivery without a collective (the one exchange of the path, the padded detections of every
- * rank's images to rank dst).  cerb_nms_deliver is cerb_nms whose `dets` / `counts` point into a slot of rank dst's
- * memory that is peer-mapped into this process (NVLink), plus four 32-bit words of protocol state:
- *   flag_remote   in dst's memory (peer-mapped): the kernel's last CTA stores there, with release semantics at system
- *                 scope and after every CTA has fenced its stores, the number of batches this rank has delivered into
- *                 the slot;
- *   ack_local     in this rank's memory, written remotely by dst (cerb_deliver_collect): batches dst has taken out of
- *                 the slot.  Before its first store the kernel waits (bounded, ~2 s) until ack >= the batches it has
- *                 written there, so a slot is never overwritten before dst has seen it;
- *   seq_local, done_local   local counters owned by the kernel (zero-initialised once by the caller).
- * cerb_deliver_collect is dst's side, a 32-thread kernel: for every rank r != dst wait until flags_local[r] exceeds
- * *collected_local, then store the new count into ack_remote[r] (rank r's ack word, peer-mapped) and advance
- * *collected_local.  Both are plain stream-ordered launches and can be captured in CUDA graphs; no NCCL kernel and no
- * host synchronisation is on the data path.
+ * Multi-GPU delivery without a collective (the one exchange of the path -- the padded detections of every
+ * rank's images reach rank dst).  Rank dst owns, per (slot, rank), a region of device memory that is peer-mapped into
+ * every writer (NVLink), and a writer signals / dst acknowledges through two 32-bit words per slot:
+ *   flag    in dst's memory (peer-mapped into the writer): batches the writer has delivered into the slot.  Stored with
+ *           release semantics at system scope by the LAST CTA of the delivering kernel, after every CTA has ordered its
+ *           stores before its completion count at GPU scope (PTX causality order is transitive across the two scopes);
+ *   ack     in the writer's memory, stored remotely by dst: batches dst has taken out of the slot.  A writer waits
+ *           (bounded, ~2 s: a lost peer must not hang the GPU) until ack >= the batches it has written there before
+ *           its first store, so a slot is never overwritten before dst has seen it;
+ *   seq, done   local counters owned by the delivering kernel (zero-initialised once by the caller);
+ *   collected   local counter owned by dst's kernel.
+ * All of it is stream-ordered kernels, capturable in CUDA graphs: no NCCL kernel and no host synchronisation is on the
+ * data path.  Three forms:
+ *
+ * cerb_nms_deliver, piggyback (push_src != NULL; what shard.PeerDelivery uses): cerb_nms writing LOCAL `dets` / `counts`
+ *   as on one GPU; at its START the launch pushes the PREVIOUS batch's packed words (dets rows then counts, left in
+ *   local staging by the previous launch: push_src -> push_dst, push_words 32-bit words, a multiple of 4, both
+ *   16-byte aligned) with 128-bit stores, and publishes that slot's flag at its END, ~50 us later, when the stores have
+ *   long landed: the fences cost nothing and the step graph has no extra node.  On rank dst (collect_flags != NULL)
+ *   CTA 0 also takes the batch the writers pushed during the previous step: thread r waits for collect_flags[r] to
+ *   exceed *collect_count and stores the acknowledgement into collect_ack[r] (rank r's ack word, peer-mapped).
+ * cerb_nms_deliver, direct (push_src == NULL, flag_remote != NULL): `dets` / `counts` ARE dst's slot; rows cross NVLink
+ *   one by one and the fences sit at the end of the NMS kernel (+7 us per step at N=2).
+ * cerb_deliver_push / cerb_deliver_collect: the two sides as kernels of their own (the last batches of a run, and
+ *   tools/side_probe.py).
  */
+typedef struct cerb_delivery {
+    const void* push_src;    /* writer, piggyback: previous batch in local staging, or NULL */
+    void* push_dst;          /* ... its slot in dst's memory (peer-mapped) */
+    size_t push_words;
+    void* flag_remote;       /* writer: the slot's flag word in dst's memory; NULL = this launch delivers nothing */
+    const void* ack_local;
+    void* seq_local;
+    void* done_local;
+    const void* collect_flags;   /* dst: local [world] flag words of the slot to take, or NULL */
+    void* collect_ack[16];       /* dst: rank r's ack word of that slot (peer-mapped); entry dst unused */
+    void* collect_count;         /* dst: local counter of that slot */
+    int world, dst;
+} cerb_delivery;
 int cerb_nms_deliver(const void* const* pred, const int* nc, int T, int B, int A, int dtype, double conf_thres,
                      double iou_thres, const int* classes, int n_classes, int agnostic, int multi_label, int max_det,
                      int max_nms, double max_wh, const void* const* smax, float* dets, int* counts, void* workspace,
-                     size_t workspace_bytes, void* flag_remote, const void* ack_local, void* seq_local, void* done_local,
-                     void* stream);
+                     size_t workspace_bytes, const cerb_delivery* delivery, void* stream);
+int cerb_deliver_push(const void* src_local, void* dst_remote, size_t n_words, void* flag_remote, const void* ack_local,
+                      void* seq_local, void* done_local, void* stream);
 int cerb_deliver_collect(const void* flags_local, void* const* ack_remote, void* collected_local, int world, int dst,
                          void* stream);
 

@@ -47,12 +47,17 @@ def main():
     dev_heads = [[x.to(dev) for x in lv] for lv in heads]
     kinds = []
     streamed = {}
-    for prefer_peer in (True, False):
-        deliv = make_delivery(len(ncs), len(mine), kw["max_det"], dev, prefer_peer=prefer_peer)
-        kinds.append(type(deliv).__name__)
+    for mode in ("peer", "peer_direct", "gather"):
+        os.environ["CERB_DELIVERY"] = mode
+        deliv = make_delivery(len(ncs), len(mine), kw["max_det"], dev)
+        kinds.append(type(deliv).__name__ + ("(direct)" if getattr(deliv, "direct", False) else ""))
         pipe = PostHeadPipeline(dev_heads, STRIDES, kw, outs=deliv.outs, delivery=deliv)
-        for rep, n_steps in enumerate((5, 4, 1, 2)):  # several runs: the flags / buffers must be reusable; 1 and 2 = the short-run graphs
+        for rep, n_steps in enumerate((5, 4, 1, 2, 3, 8)):  # several runs: the flags / buffers must be reusable; 1 and 2 = the short-run graphs
             pipe.k, pipe.pending = 0, None
+            if hasattr(deliv, "ctrl"):  # wipe rank 0's slots: a batch that is not delivered in THIS run must not pass
+                deliv.local[: deliv.ctrl].zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
             for k in range(n_steps):
                 deliv.before_write((k - 1) & 1)
                 done = pipe.step()
