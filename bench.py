@@ -356,6 +356,74 @@ def planted_line(dev):
     return out
 
 
+def head_tail_line(dev, reps=10):
+    """SURVEY 8f row 3 at the bench shape (B=64, 3 task heads, 640x640) with yolov8x head widths (c2 = 80, c3 = 320): the
+    fused tcgen05 kernel (last 1x1 convolutions of both towers + concat + decode, cerb_head_tail) against what the
+    reference runs on the same GPU (18 cuDNN 1x1 convolutions + 9 torch.cat + the decode kernel) -- CUDA-graph replays,
+    events around the replay.  Roofline: HBM (inputs read once + y and the score summary written)."""
+    import torch.nn.functional as F
+
+    from cerberusdet_b200 import ops
+    from cerberusdet_b200.synth import STRIDES
+
+    B, c2, c3 = B_PER_GPU, 80, 320
+    hw = [(IMGSZ // int(s), IMGSZ // int(s)) for s in STRIDES]
+    gen = torch.Generator(device=dev).manual_seed(3)
+    mk = lambda *shape, std=1.0: (torch.randn(*shape, generator=gen, device=dev) * std).half()  # noqa: E731
+    box = [[mk(B, c2, h, w) for h, w in hw] for _ in NCS]
+    cls = [[mk(B, c3, h, w) for h, w in hw] for _ in NCS]
+    bw = [[mk(64, c2, 1, 1, std=3.0 / c2**0.5) for _ in hw] for _ in NCS]
+    bb = [[mk(64) for _ in hw] for _ in NCS]
+    cw = [[mk(n, c3, 1, 1, std=2.0 / c3**0.5) for _ in hw] for n in NCS]
+    cb = [[mk(n) - 5.0 for _ in hw] for n in NCS]
+
+    def unfused():
+        raw = [[torch.cat((F.conv2d(box[t][l], bw[t][l], bb[t][l]), F.conv2d(cls[t][l], cw[t][l], cb[t][l])), 1) for l in range(3)]
+               for t in range(len(NCS))]
+        return ops.decode_heads(raw, STRIDES)
+
+    def fused():
+        return ops.head_tail(box, cls, bw, bb, cw, cb, STRIDES)
+
+    def timed(fn):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s), torch.cuda.graph(g, stream=s):
+            keep = fn()
+        torch.cuda.current_stream().wait_stream(s)
+        for _ in range(3):
+            g.replay()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        del keep
+        return statistics.median(ts)
+
+    in_bytes = B * ANCHORS * 2 * (c2 + c3) * len(NCS)
+    out_bytes = sum(B * ANCHORS * 2 * (4 + n) + B * n * (ANCHORS // 8) * 2 for n in NCS)
+    raw_bytes = sum(B * ANCHORS * 2 * (64 + n) for n in NCS)
+    fused_ms, unfused_ms = timed(fused), timed(unfused)
+    peak, peak_src = _peaks()
+    gbps = (in_bytes + out_bytes) / (fused_ms * 1e-3) / 1e9
+    return {"kernel": "head_tail_kernel (tcgen05.mma kind::f16, TMA, TMEM; csrc/head_tail.cu)",
+            "what": "last 1x1 convs of both towers (c2=80 -> 64, c3=320 -> nc) + concat + decode, B=64, 3 task heads, 640x640, fp16",
+            "fused_ms": fused_ms, "reference_sequence_same_gpu_ms": unfused_ms, "speedup": unfused_ms / fused_ms,
+            "images_per_s": B / (fused_ms * 1e-3), "algorithmic_bytes": in_bytes + out_bytes,
+            "raw_head_bytes_never_written_or_reread": 2 * raw_bytes,
+            "roofline": {"bound": "hbm", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak, "peak_source": peak_src}}
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -603,6 +671,10 @@ def main():
                 line["planted"] = planted_line(dev)
             except Exception as exc:  # pragma: no cover
                 line["planted"] = {"error": f"{type(exc).__name__}: {exc}"}
+            try:
+                line["head_tail"] = head_tail_line(dev)
+            except Exception as exc:  # pragma: no cover
+                line["head_tail"] = {"error": f"{type(exc).__name__}: {exc}"}
             try:
                 line["gpu_eager_reference"] = eager_reference_line(heads_dev, dev)
             except Exception as exc:  # pragma: no cover
