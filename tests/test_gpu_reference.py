@@ -319,3 +319,103 @@ def test_val_patch_process_batch_matches_reference(ref, patch):
     assert torch.equal(val_mod.process_batch(cases[0][0].cpu(), cases[0][1].cpu(), iouv.cpu()), want[0].cpu())  # CPU: reference code
     patch.uninstall()
     assert val_mod.process_batch is orig
+
+
+def test_validation_batch_statistics_equals_the_reference_loop(ref):
+    """the "Statistics per image" block of the reference validation loop (cerberusdet/val.py:321-357) executed
+    with the reference's OWN functions on CUDA tensors, image by image, against ``val_stats.validation_batch_statistics``
+    (batched rescale + one cerb_val_match launch): the tuples the loop appends to ``stats``, bit for bit."""
+    import cerberusdet.val as val_mod
+    from cerberusdet.utils.general import scale_boxes, xywh2xyxy
+
+    from cerberusdet_b200 import ops, val_stats
+
+    process_batch = getattr(val_mod.process_batch, "_cerb_reference", val_mod.process_batch)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(21)
+    B, max_det, nc = 6, 300, 4
+    img = torch.zeros(B, 3, 384, 640, device=dev)
+    ori_shape = [(480, 640), (720, 1280), (384, 640), (1000, 700), (333, 500), (640, 640)]
+    ratio_pad = []
+    for (h0, w0) in ori_shape:  # what the reference's letterbox records: ((ratio_h, ratio_w), (pad_w, pad_h))
+        r = min(384 / h0, 640 / w0)
+        ratio_pad.append(((r, r), ((640 - w0 * r) / 2, (384 - h0 * r) / 2)))
+    n_lab = [7, 0, 25, 3, 0, 12]
+    n_det = [300, 40, 0, 5, 0, 120]
+    cls_l, box_l, idx_l = [], [], []
+    dets = torch.zeros(B, max_det, 6)
+    for i in range(B):
+        cxy = 0.15 + 0.7 * torch.rand(n_lab[i], 2, generator=g)
+        wh = 0.05 + 0.25 * torch.rand(n_lab[i], 2, generator=g)
+        c = torch.randint(0, nc, (n_lab[i], 1), generator=g).float()
+        cls_l.append(c); box_l.append(torch.cat((cxy, wh), 1)); idx_l.append(torch.full((n_lab[i],), float(i)))
+        n = n_det[i]
+        if n:
+            if n_lab[i]:
+                pick = torch.randint(0, n_lab[i], (n,), generator=g)
+                lab_xyxy = torch.cat((cxy - wh / 2, cxy + wh / 2), 1)[pick] * torch.tensor([640.0, 384.0, 640.0, 384.0])
+                boxes = lab_xyxy + torch.randn(n, 4, generator=g) * 6
+                pc = c[pick, 0].clone()
+                pc[::5] = (pc[::5] + 1) % nc
+            else:
+                boxes = torch.rand(n, 4, generator=g) * 300
+                boxes[:, 2:] += boxes[:, :2]
+                pc = torch.randint(0, nc, (n,), generator=g).float()
+            conf = torch.sort(torch.rand(n, generator=g), descending=True).values
+            dets[i, :n] = torch.cat((boxes, conf[:, None], pc[:, None]), 1)
+    batch = {"img": img, "batch_idx": torch.cat(idx_l), "cls": torch.cat(cls_l), "bboxes": torch.cat(box_l),
+             "ori_shape": ori_shape, "ratio_pad": ratio_pad}
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    dets, counts = dets.to(dev), torch.tensor(n_det, dtype=torch.int32, device=dev)
+    iouv = torch.linspace(0.5, 0.95, 10, device=dev)
+    niou = iouv.numel()
+
+    # ---- the reference loop body (val.py:321-357), verbatim in structure, with the reference's own functions
+    want = []
+    out = [dets[i, : n_det[i]].clone() for i in range(B)]
+    for si, pred in enumerate(out):
+        idx = batch["batch_idx"] == si
+        cls, bbox = batch["cls"][idx], batch["bboxes"][idx]
+        nl, npr = cls.shape[0], pred.shape[0]
+        shape = batch["ori_shape"][si]
+        correct_bboxes = torch.zeros(npr, niou, dtype=torch.bool, device=dev)
+        if npr == 0:
+            if nl:
+                want.append((correct_bboxes, *torch.zeros((2, 0), device=dev), cls.squeeze(-1)))
+            continue
+        predn = pred.clone()
+        scale_boxes(batch["img"][si].shape[1:], predn[:, :4], shape, ratio_pad=batch["ratio_pad"][si])
+        if nl:
+            height, width = batch["img"].shape[2:]
+            tbox = xywh2xyxy(bbox) * torch.tensor((width, height, width, height), device=dev)
+            scale_boxes(batch["img"][si].shape[1:], tbox, shape, ratio_pad=batch["ratio_pad"][si])
+            labelsn = torch.cat((cls, tbox), 1)
+            correct_bboxes = process_batch(predn, labelsn, iouv)
+        want.append((correct_bboxes, pred[:, 4], pred[:, 5], cls.squeeze(-1)))
+
+    got = val_stats.validation_batch_statistics(dets, counts, batch, iouv)
+    assert len(got) == len(want) == 5  # image 4 has neither labels nor predictions: nothing appended (val.py:333-338)
+    for a, b in zip(got, want):
+        assert len(a) == len(b) == 4
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and x.dtype == y.dtype and x.device == y.device and torch.equal(x, y)
+    assert any(bool(t[0].any()) for t in want) and any(not bool(t[0].all()) for t in want)
+    # ratio_pad = None (the reference then derives gain and pad from the shapes): same function, same result
+    batch2 = dict(batch, ratio_pad=None)
+    got2 = val_stats.validation_batch_statistics(dets, counts, batch2, iouv)
+    want2 = []
+    for si in range(B):
+        if n_det[si] == 0:
+            continue
+        predn = dets[si, : n_det[si]].clone()
+        scale_boxes(batch["img"][si].shape[1:], predn[:, :4], ori_shape[si])
+        want2.append(predn)
+    # (the statistics tuples do not carry the boxes; compare the rescale itself through the batched helper)
+    inv_gain, px, py, w0, h0 = val_stats._scale_params((384, 640), ori_shape, [None] * B, dev)
+    scaled = val_stats._scale_boxes_batched(dets[..., :4], inv_gain, px, py, w0, h0)
+    k = 0
+    for si in range(B):
+        if n_det[si]:
+            assert torch.equal(scaled[si, : n_det[si]], want2[k][:, :4])
+            k += 1
+    assert len(got2) == len(got)

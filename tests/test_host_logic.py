@@ -370,3 +370,30 @@ def test_val_matching_matches_reference_process_batch():
         N = int(torch.randint(1, 60, (1,), generator=g))
         det, lab = _val_case(g, M, N)
         assert torch.equal(ref_val.process_batch(det, lab, iouv), match_predictions(det, lab, iouv)), trial
+
+
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
+def test_batched_rescale_equals_reference_scale_boxes_on_cpu():
+    """The rescale half of val_stats.validation_batch_statistics against the reference's own scale_boxes, with
+    and without ratio_pad, bit for bit on CPU tensors (true division there; the GPU test pins the CUDA reciprocal form)."""
+    from oracle.ref_import import load_reference
+
+    load_reference()
+    from cerberusdet.utils.general import scale_boxes
+
+    from cerberusdet_b200 import val_stats
+
+    ori = [(480, 640), (720, 1280), (333, 500), (640, 640)]
+    g = torch.Generator().manual_seed(5)
+    for with_rp in (True, False):
+        rp = []
+        for (h0, w0) in ori:
+            r = min(384 / h0, 640 / w0)
+            rp.append(((r, r), ((640 - w0 * r) / 2, (384 - h0 * r) / 2)) if with_rp else None)
+        boxes = torch.rand(len(ori), 40, 4, generator=g) * 700 - 30  # some outside the image: clip_boxes matters
+        cols = val_stats._scale_params((384, 640), ori, rp, torch.device("cpu"))
+        got = val_stats._scale_boxes_batched(boxes, *cols)
+        for i in range(len(ori)):
+            want = boxes[i].clone()
+            scale_boxes((384, 640), want, ori[i], ratio_pad=rp[i])
+            assert torch.equal(got[i], want)
