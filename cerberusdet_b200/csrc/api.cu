@@ -21,6 +21,7 @@ enum Knob {
     K_DECODE_L2HINT,  // force the L2 evict-first input policy on / off
     K_NMS_MINB,       // 1 = 128-register NMS build, 2 = 64-register build
     K_NMS_PDL,        // 0 = launch the NMS kernel without programmatic stream serialization
+    K_DECODE_PDL,     // 1 = launch the (pipelined) decode kernel WITH it: the single-stream overlapped schedule of pipeline.py
     K_CHUNK_CAP,      // lazy top-k: chunk capacity (16..4096)
     K_CHUNK_FIRST,    // lazy top-k: first chunk target
     K_HIST_SAMPLE,    // stride of the estimating histogram
@@ -32,11 +33,11 @@ enum Knob {
     K_COUNT
 };
 static const char* const kKnobName[K_COUNT] = {"decode_pipe", "decode_order", "decode_vec", "decode_l2hint", "nms_minb",
-                                               "nms_pdl",     "chunk_cap",    "chunk_first", "hist_sample",  "ht_order",
+                                               "nms_pdl",     "decode_pdl",     "chunk_cap",    "chunk_first", "hist_sample",  "ht_order",
                                                "ht_stages",   "ht_groups",   "push_ctas",
                                                "push_mode"};
 static const char* const kKnobEnv[K_COUNT] = {"CERB_DEBUG_DECODE_PIPE", "CERB_DEBUG_DECODE_ORDER", "CERB_DEBUG_DECODE_VEC",
-                                              "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL",
+                                              "CERB_DEBUG_DECODE_L2HINT", "CERB_DEBUG_NMS_MINB", "CERB_DEBUG_NMS_PDL", "CERB_DEBUG_DECODE_PDL",
                                               nullptr, nullptr, nullptr, "CERB_DEBUG_HT_ORDER", "CERB_DEBUG_HT_STAGES",
                                               "CERB_DEBUG_HT_GROUPS", "CERB_DEBUG_PUSH_CTAS", "CERB_DEBUG_PUSH_MODE"};
 struct KnobTable {
@@ -197,6 +198,8 @@ static int decode_common(const void* const* lvl, const void* const* cls_lvl, con
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess)
             P.l2_evict_first = out_bytes <= (size_t)l2 / 4 * 3;
         (void)knob(K_DECODE_L2HINT, &P.l2_evict_first);
+        P.pdl = 0;
+        (void)knob(K_DECODE_PDL, &P.pdl);
     }
     cudaError_t e = cudaErrorInvalidConfiguration;
     // software-pipelined kernel (decode_pipe.cu) whenever every row allows 16-byte vectors, else (or with the

@@ -22,6 +22,9 @@ struct DecodeParams {
     int row_blocks_per_part[CERB_MAX_TASKS * CERB_MAX_LEVELS];  // ceil(B * nvecp / threads)
     void* smax[CERB_MAX_TASKS];  // optional score summary [B, nc, A/V]: max of every 16-byte score vector
     int l2_evict_first;          // pipelined kernel: read the raw heads with an L2 evict-first policy (outputs fit in L2)
+    int pdl;                     // host only: launch with programmatic stream serialization -- the grid may start as soon as the
+                                 // kernel before it in the stream has released its dependents (the NMS kernel of the PREVIOUS
+                                 // batch does so at entry); the decode reads nothing that kernel writes, so it never waits
     int interleave_parts;        // block order: 0 parts contiguous per (task, level), 1 interleaved, 2 all DFL blocks first, then all class blocks
 };
 cudaError_t cerb_launch_decode(DecodeParams& P, int dtype, int vec, cudaStream_t stream);

@@ -247,8 +247,24 @@ template <typename T, int VEC, int IPT, int CIPT> static cudaError_t launch_pipe
     cudaError_t e = cudaFuncSetAttribute(decode_pipe_kernel<T, VEC, IPT, CIPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    decode_pipe_kernel<T, VEC, IPT, CIPT><<<blocks, DEC_THREADS, smem, stream>>>(q);
-    return cudaGetLastError();
+    if (!P.pdl) {
+        decode_pipe_kernel<T, VEC, IPT, CIPT><<<blocks, DEC_THREADS, smem, stream>>>(q);
+        return cudaGetLastError();
+    }
+    // overlapped schedule on ONE stream (pipeline.py): NMS(k-1), then this launch with the programmatic attribute -- its CTAs
+    // are dispatched once every CTA of the NMS kernel has started, never before (the order that overlaps best, made
+    // deterministic), and run beside it
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(DEC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_pipe_kernel<T, VEC, IPT, CIPT>, q);
 }
 
 // Items per thread (DFL rows, class rows) of the shipped instantiations: fp16 2 / PIPE_CIPT_F16, fp32 1 / 1

@@ -705,6 +705,9 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
     BLOCK_T_START
+    // a kernel launched behind this one with the programmatic attribute (the NEXT batch's decode in the single-stream
+    // overlapped schedule) may start as soon as every CTA of this grid is running
+    asm volatile("griddepcontrol.launch_dependents;");
     if (P.push_src != nullptr) {
         // piggyback delivery: push the PREVIOUS batch (complete in local staging since the previous launch) into rank
         // dst's slot before anything else; the fences that publish it are at the very end of this kernel, by when

@@ -27,6 +27,13 @@ from . import ops
 # on a third branch of the step graph; "after" = small graphs replayed after the step graph; "off" = never (nothing is
 # delivered: timing experiments only)
 _SIDE = os.environ.get("CERB_SIDE", "piggyback")
+_DUMMY3 = os.environ.get("CERB_DUMMY3", "0") == "1"
+# how the two kernels of an overlapped step are made concurrent: "pdl" = ONE stream, NMS(k-1) then decode(k) launched with
+# the programmatic-serialization attribute (its CTAs are dispatched as soon as every NMS CTA is running, never before: the
+# NMS CTAs, 109 KB of shared memory each, must be placed first or they wait for decode CTAs to drain); "streams" = two
+# graph branches (the launch order of two root nodes is a race: 0.098 or 0.106 ms per step, profiles/r02_multi_gpu.md)
+_SCHEDULE = os.environ.get("CERB_SCHEDULE", "pdl")
+_STANDALONE = ("branch3", "last3", "pre_nms", "post_nms", "post_decode")  # where the stand-alone delivery kernel sits in the step graph
 
 
 class PostHeadPipeline:
@@ -66,6 +73,7 @@ class PostHeadPipeline:
         with torch.cuda.device(self.device):
             self.ybuf = [ops.decode_buffers(self.heads) for _ in range(2)]
             self.sa, self.sb, self.sc = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+            self._dummy = torch.zeros(1, device=self.device)
             # eager warm-up of both kernels (module load, function attributes) before anything is captured
             ys = ops.decode_heads(self.heads, self.strides, out=self.ybuf[0])
             ops.nms_batched(ys, out=self.outs[0], **self.kw)
@@ -92,8 +100,16 @@ class PostHeadPipeline:
             torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ graph construction
-    def _decode(self, p):
-        return ops.decode_heads(self.heads, self.strides, out=self.ybuf[p])
+    def _decode(self, p, pdl: bool = False):
+        if not pdl:
+            return ops.decode_heads(self.heads, self.strides, out=self.ybuf[p])
+        from . import _lib
+
+        _lib.debug_set("decode_pdl", 1)  # thread-local launch option of the C ABI (include/cerb_post.h)
+        try:
+            return ops.decode_heads(self.heads, self.strides, out=self.ybuf[p])
+        finally:
+            _lib.debug_set("decode_pdl", 0)
 
     def _nms(self, p, piggyback: bool = False):
         T = len(self.heads)
@@ -124,27 +140,49 @@ class PostHeadPipeline:
         batch j-1, rank dst's launch for batch j takes batch j-2.  CERB_SIDE=branch (tools/ A/B) puts the stand-alone
         kernels on a third branch instead."""
         dv = self.delivery
-        branch = side and _SIDE == "branch3" and (dv.rank == dv.dst or not dv.direct)
-        piggy = side and not branch
+        standalone = side and _SIDE in _STANDALONE and (dv.rank == dv.dst or not dv.direct)
+        piggy = side and not standalone
+
+        def side_kernel():
+            if dv.rank == dv.dst:
+                dv.collect(1 - dec)
+            else:
+                dv.push(dec)
+
         g = torch.cuda.CUDAGraph()
         self.sa.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.sa):
             with torch.cuda.graph(g, stream=self.sa):
-                if self.overlap or dec is None or nms_of is None:
+                if self.overlap and nms_of is not None and dec is not None and _SCHEDULE == "pdl" and not standalone:
+                    self._nms(nms_of, piggy)         # NMS of the previous batch: releases its dependents at entry
+                    self._decode(dec, pdl=True)      # runs beside it; reads nothing it writes, so it never waits for it
+                elif self.overlap or dec is None or nms_of is None:
                     if nms_of is not None and dec is not None:
                         self.sb.wait_stream(self.sa)
-                        if branch:
+                        if standalone and _SIDE == "branch3":      # third branch, created first
                             self.sc.wait_stream(self.sa)
                             with torch.cuda.stream(self.sc):
-                                if dv.rank == dv.dst:
-                                    dv.collect(1 - dec)
-                                else:
-                                    dv.push(dec)
+                                side_kernel()
+                        if standalone and _SIDE == "last3":        # third branch, created after the two big kernels
+                            self.sc.wait_stream(self.sa)
                         with torch.cuda.stream(self.sb):
+                            if standalone and _SIDE == "pre_nms":
+                                side_kernel()
                             self._nms(nms_of, piggy)
+                            if standalone and _SIDE == "post_nms":
+                                side_kernel()
                         self._decode(dec)
+                        if standalone and _SIDE == "post_decode":
+                            side_kernel()
+                        if standalone and _SIDE == "last3":
+                            with torch.cuda.stream(self.sc):
+                                side_kernel()
+                        if _DUMMY3 and not standalone:  # tools/ experiment: an (almost) empty third branch, created last
+                            self.sc.wait_stream(self.sa)
+                            with torch.cuda.stream(self.sc):
+                                self._dummy.add_(1)
                         self.sa.wait_stream(self.sb)
-                        if branch:
+                        if (standalone and _SIDE in ("branch3", "last3")) or (_DUMMY3 and not standalone):
                             self.sa.wait_stream(self.sc)
                     elif dec is not None:
                         self._decode(dec)
@@ -207,7 +245,7 @@ class PostHeadPipeline:
             self.pending = p
             self._pushed = self._collected = 0  # batches of this run already pushed (writer) / collected (dst)
             return None
-        in_launch = self.delivery is not None and k >= 3 and _SIDE in ("piggyback", "branch3")
+        in_launch = self.delivery is not None and k >= 3 and (_SIDE == "piggyback" or _SIDE in _STANDALONE)
         if timed is not None:
             g, _ = self.timed[timed]
             if self.timed_parity[timed] != p:

@@ -274,7 +274,10 @@ int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_row
  * library stays re-entrant); cerb_debug_reset() drops every override of the calling thread.  Results never depend
  * on a knob: the parity tests run the alternatives against each other.  Knobs: "decode_pipe" (0 = register-resident
  * decode kernel instead of the pipelined one), "decode_order", "decode_vec", "decode_l2hint", "nms_minb" (1 | 2: the
- * 128- / 64-register NMS build), "nms_pdl" (0 = no programmatic dependent launch), "chunk_cap", "chunk_first",
+ * 128- / 64-register NMS build), "nms_pdl" (0 = no programmatic dependent launch), "decode_pdl" (1 = the decode
+ * launch carries the programmatic-serialization attribute: behind an NMS launch of another batch in the same stream it starts
+ * as soon as every NMS CTA is running -- the single-stream overlapped schedule of pipeline.py; the decode reads nothing the
+ * kernel before it writes), "chunk_cap", "chunk_first",
  * "hist_sample", "ht_order" (head-tail kernel: 0 = tiles dealt round-robin to the CTAs, 1 = contiguous runs), "ht_stages"
  * (cap on its activation ring depth), "ht_groups" (its epilogue warp groups, 1 | 2).
  */

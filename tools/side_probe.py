@@ -66,8 +66,15 @@ class LoopbackDelivery:
 def run(steps, delivery_mode):
     dev = torch.device("cuda", 0)
     heads = [[x.to(dev) for x in lv] for lv in synth_heads(range(64), NCS, 640, torch.float16, "iid", cfg=3)]
-    dv = LoopbackDelivery(len(NCS), 64, KW["max_det"], dev, delivery_mode) if delivery_mode != "none" else None
-    pipe = PostHeadPipeline(heads, STRIDES, KW, delivery=dv)
+    dv = LoopbackDelivery(len(NCS), 64, KW["max_det"], dev, delivery_mode) if delivery_mode not in ("none", "none_pad", "none_outs") else None
+    pad = None
+    outs = None
+    if delivery_mode == "none_pad":    # the same allocations as LoopbackDelivery, unused: does buffer placement alone change the step time?
+        pad = LoopbackDelivery(len(NCS), 64, KW["max_det"], dev, "full")
+    if delivery_mode == "none_outs":   # ... or writing the detections into one packed buffer per slot?
+        pad = LoopbackDelivery(len(NCS), 64, KW["max_det"], dev, "full")
+        outs = pad.outs
+    pipe = PostHeadPipeline(heads, STRIDES, KW, delivery=dv, outs=outs)
 
     def loop(n):
         pipe.k, pipe.pending = 0, None
@@ -97,11 +104,16 @@ def main():
     if args.one:
         ms, ok = run(args.steps, args.one)
         print(json.dumps({"mode": args.one, "side": os.environ.get("CERB_SIDE", "branch"), "push_mode": os.environ.get("CERB_DEBUG_PUSH_MODE"),
-                          "push_ctas": os.environ.get("CERB_DEBUG_PUSH_CTAS"), "ms_per_step": round(ms, 5), "delivered": ok}))
+                          "push_ctas": os.environ.get("CERB_DEBUG_PUSH_CTAS"), "dummy3": os.environ.get("CERB_DUMMY3"), "ms_per_step": round(ms, 5), "delivered": ok}))
         return
     # (a collect without a matching flag-setting push would sit out its 2 s bound every step: never combine those)
-    runs = (("none", {}), ("full", {}), ("push_only", {"CERB_DEBUG_PUSH_MODE": "1"}), ("full", {"CERB_DEBUG_PUSH_MODE": "2"}),
-            ("full", {"CERB_DEBUG_PUSH_CTAS": "4"}), ("full", {"CERB_DEBUG_PUSH_CTAS": "128"}), ("none", {}), ("full", {}))
+    if os.environ.get("SIDE_PROBE_SET", "placement") == "dummy":  # does a third branch help even without a delivery?  (bimodal step times)
+        runs = (("none", {}), ("none_pad", {}), ("none_outs", {}), ("full", {"CERB_SIDE": "last3"}), ("full", {"CERB_SIDE": "last3", "CERB_DEBUG_PUSH_MODE": "2"})) * 2
+    elif os.environ.get("SIDE_PROBE_SET", "placement") == "placement":  # where in the step graph does the side kernel hurt least?
+        runs = (("none", {}),) + tuple(("full", {"CERB_SIDE": v}) for v in ("branch3", "last3", "pre_nms", "post_nms", "post_decode")) + (("none", {}),)
+    else:  # what inside the side kernels costs? (a collect without a matching flag-setting push would sit out its 2 s bound every step)
+        runs = (("none", {}), ("full", {}), ("push_only", {"CERB_DEBUG_PUSH_MODE": "1"}), ("full", {"CERB_DEBUG_PUSH_MODE": "2"}),
+                ("full", {"CERB_DEBUG_PUSH_CTAS": "4"}), ("full", {"CERB_DEBUG_PUSH_CTAS": "128"}), ("none", {}), ("full", {}))
     for mode, extra in runs:
         env = dict(os.environ, **extra)
         try:
