@@ -9,8 +9,9 @@ max_nms 30000 / max_det 300).  N>1: every rank owns B images (weak scaling; N=8 
 detections of every batch reach rank 0 inside the timed region.
 
 How the timed region runs (cerberusdet_b200/pipeline.py): a two-stage software pipeline replayed from CUDA graphs --
-step k decodes batch k while the NMS of batch k-1 runs on a second stream; a final flush does the last NMS, so K steps
-are exactly K decode launches + K NMS launches.  32 of the K steps (16 when K < 128) are "instrumented" replays of the
+step k decodes batch k while the NMS of batch k-1 runs beside it (one stream: the NMS kernel releases its dependents at
+entry and the decode launch carries the programmatic-serialization attribute); a final flush does the last NMS, so K
+steps are exactly K decode launches + K NMS launches.  32 of the K steps (16 when K < 128) are "instrumented" replays of the
 same two kernels in serial order with timing events recorded by the graph itself around each kernel: that is where
 `roofline` (the decode kernel alone on the GPU) comes from; they cost ~13 us more than an overlapped step each.
 
@@ -640,7 +641,8 @@ def main():
         line["e2e"] = {"value": B_PER_GPU * world * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps}
         line["gpu_launches"] = 2 * steps  # one decode_pipe_kernel + one nms_kernel per step, nothing else of ours
-        line["launch_mode"] = "cuda_graphs, serial" if args.serial else "cuda_graphs, decode(k) overlapped with NMS(k-1) on two streams"
+        line["launch_mode"] = "cuda_graphs, serial" if args.serial else ("cuda_graphs, one stream per step: NMS(k-1), then decode(k) launched programmatically "
+                                                                        "beside it (griddepcontrol / programmatic stream serialization)")
         line["clocks"] = clk.summary()
         line["equality"] = equality
         if per_rank is not None:
