@@ -34,6 +34,8 @@ EXPORTS = (
     "cerb_val_match",
     "cerb_bbox_decode_fwd",
     "cerb_bbox_decode_bwd",
+    "cerb_tal_workspace_bytes",
+    "cerb_tal_assign",
     "cerb_debug_set",
     "cerb_debug_reset",
     "cerb_debug_set_chunking",
@@ -112,6 +114,11 @@ def load() -> ctypes.CDLL:
     lib.cerb_bbox_decode_fwd.argtypes = [vp, vp, lg, i, i, i, vp, vp]
     lib.cerb_bbox_decode_bwd.restype = i
     lib.cerb_bbox_decode_bwd.argtypes = [vp, vp, lg, i, i, vp, vp]
+    if hasattr(lib, "cerb_tal_assign") or "CERB_LIB" not in os.environ:
+        lib.cerb_tal_workspace_bytes.restype = sz
+        lib.cerb_tal_workspace_bytes.argtypes = [i, i, i, i]
+        lib.cerb_tal_assign.restype = i
+        lib.cerb_tal_assign.argtypes = [vp] * 6 + [i] * 5 + [d, d, d, i] + [vp] * 6 + [sz, vp]
     if hasattr(lib, "cerb_debug_set") or "CERB_LIB" not in os.environ:  # (tools/ A/B runs may load an older build)
         lib.cerb_debug_set.restype = i
         lib.cerb_debug_set.argtypes = [ctypes.c_char_p, i]

@@ -696,3 +696,43 @@ def bbox_decode(anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> torch.T
     """Drop-in for the reference's ``Loss.bbox_decode(anchor_points, pred_dist)`` with ``use_dfl`` (utils/loss.py:126-131):
     ``pred_dist [B, A, 64]`` -> ``[B, A, 4]`` (x1, y1, x2, y2) in grid units, differentiable w.r.t. ``pred_dist``."""
     return _BboxDecode.apply(anchor_points, pred_dist)
+
+
+# ----------------------------------------------------------------------------- TAL assigner (SURVEY 8f-4)
+def tal_assign(pd_scores: torch.Tensor, pd_bboxes: torch.Tensor, anc_points: torch.Tensor, gt_labels: torch.Tensor,
+               gt_bboxes: torch.Tensor, mask_gt: torch.Tensor, topk: int = 10, num_classes: Optional[int] = None,
+               alpha: float = 0.5, beta: float = 6.0, eps: float = 1e-9):
+    """``TaskAlignedAssigner.forward`` (reference utils/tal.py:56-178) in three launches (``cerb_tal_assign``).
+    ``pd_scores [B, A, C]`` fp16 | fp32, ``pd_bboxes [B, A, 4]`` fp32 xyxy pixels, ``anc_points [A, 2]``, ``gt_labels [B, G, 1]``,
+    ``gt_bboxes [B, G, 4]``, ``mask_gt [B, G, 1]``.  Returns ``(target_labels [B, A] int64, target_bboxes [B, A, 4],
+    target_scores [B, A, C] fp32, fg_mask [B, A] bool, target_gt_idx [B, A] int64)``.  ``G == 0`` is the caller's early
+    return in the reference (tal.py:89-93) and raises ``ValueError`` here."""
+    lib = _lib.load()
+    _require_cuda(pd_scores, "pd_scores")
+    B, A, C = (int(v) for v in pd_scores.shape)
+    G = int(gt_bboxes.shape[1])
+    if num_classes is not None and int(num_classes) != C:
+        raise ValueError(f"pd_scores has {C} classes, the assigner {num_classes}")
+    if G == 0:
+        raise ValueError("tal_assign needs at least one (padded) ground-truth box per image; the reference returns early for none")
+    dev = pd_scores.device
+    code = _dtype_code(pd_scores)
+    f32 = lambda t, shape: t.to(device=dev, dtype=torch.float32).reshape(shape).contiguous()  # noqa: E731
+    sc = pd_scores.contiguous()
+    pb, an = f32(pd_bboxes, (B, A, 4)), f32(anc_points, (A, 2))
+    gl, gb, mg = f32(gt_labels, (B, G)), f32(gt_bboxes, (B, G, 4)), f32(mask_gt, (B, G))
+    labels = torch.empty((B, A), dtype=torch.int64, device=dev)
+    bboxes = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, A, C), dtype=torch.float32, device=dev)
+    fg = torch.empty((B, A), dtype=torch.bool, device=dev)
+    gidx = torch.empty((B, A), dtype=torch.int64, device=dev)
+    ws_bytes = int(lib.cerb_tal_workspace_bytes(B, A, G, int(topk)))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cerb_tal_assign(sc.data_ptr(), pb.data_ptr(), an.data_ptr(), gl.data_ptr(), gb.data_ptr(), mg.data_ptr(), B, A, C, G,
+                                 int(topk), float(alpha), float(beta), float(eps), code, labels.data_ptr(), bboxes.data_ptr(),
+                                 scores.data_ptr(), fg.data_ptr(), gidx.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+    _lib.check(rc)
+    for t in (sc, pb, an, gl, gb, mg, ws):
+        t.record_stream(torch.cuda.current_stream(dev))
+    return labels, bboxes, scores, fg, gidx

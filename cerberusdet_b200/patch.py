@@ -44,7 +44,8 @@ def install(import_all: bool = False, train: bool = False, val: bool = False) ->
     """Patch the reference modules that are importable.  ``import_all`` also imports ``val`` /
     ``detect`` / ``cerberusdet_inference`` (they pull in the whole data pipeline); by default only
     modules already imported, plus ``models.yolo`` and ``utils.general``, are touched.  ``train`` also rebinds
-    ``Loss.bbox_decode`` (imports ``cerberusdet.utils.loss``), ``val`` the validation matching (imports
+    ``Loss.bbox_decode``, ``TaskAlignedAssigner.forward`` and the loss module's ``make_anchors`` (imports
+    ``cerberusdet.utils.loss``), ``val`` the validation matching (imports
     ``cerberusdet.val``).  Calling it again adds whatever is not patched yet (e.g. ``install()`` then
     ``install(train=True)``)."""
     import torch
@@ -121,6 +122,45 @@ def install(import_all: bool = False, train: bool = False, val: bool = False) ->
 
             bbox_decode._cerb_reference = reference_bbox_decode
             patch_once(loss_mod.Loss, "bbox_decode", bbox_decode, "cerberusdet.utils.loss.Loss.bbox_decode")
+        # the assigner the loss calls right after (utils/loss.py:160-162): three launches instead of ~60
+        tal_mod = importlib.import_module("cerberusdet.utils.tal")
+        if not hasattr(tal_mod.TaskAlignedAssigner.forward, "_cerb_reference"):
+            reference_assign = tal_mod.TaskAlignedAssigner.forward
+
+            @torch.no_grad()
+            def forward(self, pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt):
+                on_path = (pd_scores.is_cuda and pd_scores.dtype in (torch.float16, torch.float32) and pd_scores.dim() == 3
+                           and pd_bboxes.dtype == torch.float32 and gt_bboxes.dtype == torch.float32 and gt_bboxes.dim() == 3
+                           and 0 < gt_bboxes.size(1) <= 1024 and self.topk <= min(16, pd_scores.size(1))
+                           and pd_scores.size(2) == self.num_classes)
+                if not on_path:  # CPU tensors, no boxes at all (the reference's early return), exotic shapes
+                    return reference_assign(self, pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt)
+                self.bs, self.n_max_boxes = pd_scores.size(0), gt_bboxes.size(1)  # attributes the reference sets (tal.py:86-87)
+                return _ops.tal_assign(pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt, self.topk,
+                                       self.num_classes, self.alpha, self.beta, self.eps)
+
+            forward._cerb_reference = reference_assign
+            patch_once(tal_mod.TaskAlignedAssigner, "forward", forward, "cerberusdet.utils.tal.TaskAlignedAssigner.forward")
+        # make_anchors is rebuilt on every loss call (utils/loss.py:149: ~12 small launches); the result depends on the
+        # feature shapes, strides, dtype and device only
+        if not hasattr(loss_mod.make_anchors, "_cerb_reference"):
+            reference_make_anchors = loss_mod.make_anchors
+            cache = {}
+
+            def make_anchors(feats, strides, grid_cell_offset=0.5):
+                st = strides.tolist() if torch.is_tensor(strides) and not strides.is_cuda else None
+                if st is None or feats is None:  # (a device-resident stride tensor would cost a sync per call to key on)
+                    return reference_make_anchors(feats, strides, grid_cell_offset)
+                key = (tuple(tuple(f.shape[2:]) for f in feats[: len(st)]), tuple(st), feats[0].dtype, feats[0].device, float(grid_cell_offset))
+                hit = cache.get(key)
+                if hit is None:
+                    if len(cache) > 16:
+                        cache.clear()
+                    hit = cache[key] = reference_make_anchors(feats, strides, grid_cell_offset)
+                return hit
+
+            make_anchors._cerb_reference = reference_make_anchors
+            patch_once(loss_mod, "make_anchors", make_anchors, "cerberusdet.utils.loss.make_anchors")
     if val:
         from . import val_stats as _val_stats
 

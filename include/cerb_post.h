@@ -270,6 +270,29 @@ int cerb_bbox_decode_bwd(const void* pred_dist, const void* grad_out, long n_row
                          void* grad_pred_dist, void* stream);
 
 /*
+ * The training-time sibling's caller: TaskAlignedAssigner.forward (cerberusdet/utils/tal.py:56-178, with
+ * select_candidates_in_gts :13-28, select_highest_overlaps :31-53 and bbox_iou(CIoU=True) of utils/metrics.py:373-408), as
+ * called by the loss at cerberusdet/utils/loss.py:160-162, in three launches.
+ *
+ *   pd_scores     [B, A, C] sigmoid scores, fp16 | fp32 (score_dtype)      pd_bboxes   [B, A, 4] xyxy pixels, fp32
+ *   anc_points    [A, 2] anchor centres in pixels, fp32
+ *   gt_labels     [B, G] class ids as floats, gt_bboxes [B, G, 4] xyxy pixels, mask_gt [B, G] 1 = real box, 0 = padding
+ *   topk (<= 16), alpha, beta, eps: the assigner's attributes (10, 0.5, 6.0, 1e-9 in the reference, loss.py:100-105)
+ *   out: target_labels [B, A] int64, target_bboxes [B, A, 4] fp32, target_scores [B, A, C] fp32, fg_mask [B, A] bool
+ *        (one byte each), target_gt_idx [B, A] int64 -- exactly the five tensors forward returns
+ *   workspace: cerb_tal_workspace_bytes(B, A, G, topk) bytes of device memory
+ * G >= 1 (the reference returns early for G == 0, tal.py:89-93: the caller keeps that branch), G <= 1024.
+ * Equal metrics rank by anchor index ascending -- the reference's torch.topk (:140) leaves their order unspecified; it
+ * only matters for boxes with fewer than topk positive-metric anchors AND anchors inside whose CIoU is <= 0.
+ */
+size_t cerb_tal_workspace_bytes(int B, int A, int G, int topk);
+int cerb_tal_assign(const void* pd_scores, const float* pd_bboxes, const float* anc_points, const float* gt_labels,
+                    const float* gt_bboxes, const float* mask_gt, int B, int A, int C, int G, int topk, double alpha,
+                    double beta, double eps, int score_dtype, long long* target_labels, float* target_bboxes,
+                    float* target_scores, unsigned char* fg_mask, long long* target_gt_idx, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/*
  * Test / tools hooks.  cerb_debug_set(name, value) overrides one internal choice FOR THE CALLING THREAD (so the
  * library stays re-entrant); cerb_debug_reset() drops every override of the calling thread.  Results never depend
  * on a knob: the parity tests run the alternatives against each other.  Knobs: "decode_pipe" (0 = register-resident

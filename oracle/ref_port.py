@@ -30,6 +30,7 @@ agree.
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import subprocess
 from typing import List, Optional, Sequence, Tuple
@@ -266,3 +267,127 @@ def head_tail_port(box_feats: Sequence[torch.Tensor], cls_feats: Sequence[torch.
         raw.append(torch.cat((F.conv2d(box_feats[l], box_w[l], box_b[l]), F.conv2d(cls_feats[l], cls_w[l], cls_b[l])), 1))
     nc = int(cls_w[0].shape[0])
     return decode_port(raw, nc, strides), raw
+
+
+# --------------------------------------------------------------------------- TAL assigner (the training-time sibling's caller)
+def ciou_port(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """``bbox_iou(box1, box2, xywh=False, CIoU=True)`` (utils/metrics.py:373-408), one torch op per reference op."""
+    b1_x1, b1_y1, b1_x2, b1_y2 = box1.chunk(4, -1)
+    b2_x1, b2_y1, b2_x2, b2_y2 = box2.chunk(4, -1)
+    w1, h1 = b1_x2 - b1_x1, b1_y2 - b1_y1 + eps
+    w2, h2 = b2_x2 - b2_x1, b2_y2 - b2_y1 + eps
+    inter = (b1_x2.minimum(b2_x2) - b1_x1.maximum(b2_x1)).clamp(0) * (b1_y2.minimum(b2_y2) - b1_y1.maximum(b2_y1)).clamp(0)
+    union = w1 * h1 + w2 * h2 - inter + eps
+    iou = inter / union
+    cw = b1_x2.maximum(b2_x2) - b1_x1.minimum(b2_x1)
+    ch = b1_y2.maximum(b2_y2) - b1_y1.minimum(b2_y1)
+    c2 = cw**2 + ch**2 + eps
+    rho2 = ((b2_x1 + b2_x2 - b1_x1 - b1_x2) ** 2 + (b2_y1 + b2_y2 - b1_y1 - b1_y2) ** 2) / 4
+    v = (4 / math.pi**2) * (torch.atan(w2 / h2) - torch.atan(w1 / h1)).pow(2)
+    alpha = v / (v - iou + (1 + eps))
+    return iou - (rho2 / c2 + v * alpha)
+
+
+def tal_assign_port(pd_scores: torch.Tensor, pd_bboxes: torch.Tensor, anc_points: torch.Tensor, gt_labels: torch.Tensor,
+                    gt_bboxes: torch.Tensor, mask_gt: torch.Tensor, topk: int = 10, num_classes: int = 80, alpha: float = 0.5,
+                    beta: float = 6.0, eps: float = 1e-9):
+    """``TaskAlignedAssigner.forward`` (utils/tal.py:56-178, with ``select_candidates_in_gts`` :13-28 and
+    ``select_highest_overlaps`` :31-53) restated stage by stage.  One thing is made canonical: the reference's
+    ``torch.topk`` (:140) leaves the order of EQUAL metrics unspecified; here ties go to the lower anchor index.  That
+    only matters when a ground-truth box has fewer than ``topk`` anchors with a positive metric AND anchors inside it
+    whose metric is exactly 0 (CIoU <= 0): which of those become positives is arbitrary in the reference.
+    ``ambiguous [B, G]`` (last return value) flags those boxes so that tests compare the others.
+
+    Returns ``(target_labels [B, A] int64, target_bboxes [B, A, 4], target_scores [B, A, C], fg_mask [B, A] bool,
+    target_gt_idx [B, A] int64, ambiguous [B, G] bool)``."""
+    bs, n_max = pd_scores.size(0), gt_bboxes.size(1)
+    A = pd_scores.size(1)
+    if n_max == 0:
+        return (torch.full_like(pd_scores[..., 0], num_classes), torch.zeros_like(pd_bboxes), torch.zeros_like(pd_scores),
+                torch.zeros_like(pd_scores[..., 0]), torch.zeros_like(pd_scores[..., 0]), torch.zeros((bs, 0), dtype=torch.bool))
+    # get_box_metrics (:121-130)
+    bidx = torch.arange(bs).view(-1, 1).repeat(1, n_max)
+    lab = gt_labels.long().squeeze(-1)
+    bbox_scores = pd_scores[bidx, :, lab]  # [B, G, A]
+    overlaps = ciou_port(gt_bboxes.unsqueeze(2), pd_bboxes.unsqueeze(1)).squeeze(3).clamp(0)
+    align_metric = bbox_scores.pow(alpha) * overlaps.pow(beta)
+    # select_candidates_in_gts (:13-28)
+    lt, rb = gt_bboxes.view(-1, 1, 4).chunk(2, 2)
+    deltas = torch.cat((anc_points[None] - lt, rb - anc_points[None]), dim=2).view(bs, n_max, A, -1)
+    mask_in_gts = deltas.amin(3).gt_(eps)
+    # select_topk_candidates (:132-151), ties to the lower anchor index
+    metrics = align_metric * mask_in_gts
+    order = torch.sort(metrics, dim=-1, descending=True, stable=True).indices  # stable: equal values keep index order
+    topk_idxs = order[..., :topk]
+    topk_mask = mask_gt.repeat([1, 1, topk]).bool()
+    topk_idxs = torch.where(topk_mask, topk_idxs, 0)
+    is_in_topk = F.one_hot(topk_idxs, A).sum(-2)
+    is_in_topk = torch.where(is_in_topk > 1, 0, is_in_topk).to(metrics.dtype)
+    mask_pos = is_in_topk * mask_in_gts * mask_gt
+    n_positive = ((metrics > 0).sum(-1))
+    n_zero_inside = ((mask_in_gts > 0) & (metrics == 0)).sum(-1)
+    ambiguous = (n_positive < topk) & (n_zero_inside > 0) & (mask_gt.squeeze(-1) > 0)
+    # select_highest_overlaps (:31-53)
+    fg_mask = mask_pos.sum(-2)
+    if fg_mask.max() > 1:
+        mask_multi = (fg_mask.unsqueeze(1) > 1).repeat([1, n_max, 1])
+        is_max = F.one_hot(overlaps.argmax(1), n_max).permute(0, 2, 1).to(overlaps.dtype)
+        mask_pos = torch.where(mask_multi, is_max, mask_pos)
+        fg_mask = mask_pos.sum(-2)
+    target_gt_idx = mask_pos.argmax(-2)
+    # get_targets (:153-178)
+    flat_idx = target_gt_idx + torch.arange(bs, dtype=torch.int64)[..., None] * n_max
+    target_labels = gt_labels.long().flatten()[flat_idx]
+    target_bboxes = gt_bboxes.view(-1, 4)[flat_idx]
+    target_scores = F.one_hot(target_labels, num_classes)
+    target_scores = torch.where(fg_mask[:, :, None].repeat(1, 1, num_classes) > 0, target_scores, 0)
+    # normalise (:103-108)
+    align_metric = align_metric * mask_pos
+    pos_align = align_metric.amax(-1, keepdim=True)
+    pos_ov = (overlaps * mask_pos).amax(-1, keepdim=True)
+    norm = (align_metric * pos_ov / (pos_align + eps)).amax(-2).unsqueeze(-1)
+    return target_labels, target_bboxes, target_scores * norm, fg_mask.bool(), target_gt_idx, ambiguous
+
+
+def tal_case(seed: int, bs: int, level_hw, strides, nc: int, n_gt: int, noise: float = 4.0, score_dtype=torch.float32):
+    """Seeded inputs of ``TaskAlignedAssigner.forward`` as the loss builds them (utils/loss.py:139-162): anchor points in
+    pixels, ground-truth boxes (a few of them heavily overlapping, padded per image with ``mask_gt = 0``), predicted
+    boxes = for every anchor the first ground truth that contains it, jittered (so overlaps are positive where it
+    matters), and sigmoid-like scores."""
+    g = torch.Generator().manual_seed(seed)
+    pts = []
+    for (h, w), s in zip(level_hw, strides):
+        sy, sx = torch.meshgrid(torch.arange(h, dtype=torch.float32) + 0.5, torch.arange(w, dtype=torch.float32) + 0.5, indexing="ij")
+        pts.append(torch.stack((sx, sy), -1).view(-1, 2) * s)
+    anc = torch.cat(pts)
+    A = anc.shape[0]
+    H, W = level_hw[0][0] * strides[0], level_hw[0][1] * strides[0]
+    counts = torch.randint(max(n_gt // 3, 1), n_gt + 1, (bs,), generator=g)
+    counts[0] = n_gt
+    gt_bboxes = torch.zeros(bs, n_gt, 4)
+    gt_labels = torch.zeros(bs, n_gt, 1)
+    mask_gt = torch.zeros(bs, n_gt, 1)
+    for b in range(bs):
+        n = int(counts[b])
+        wh = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.35, H * 0.35]) + 12.0
+        cxy = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.8, H * 0.8]) + torch.tensor([W * 0.1, H * 0.1])
+        if n >= 4:  # two heavily overlapping pairs: anchors claimed by two boxes
+            cxy[1] = cxy[0] + 3.0
+            wh[1] = wh[0] * 1.1
+            cxy[3] = cxy[2] - 2.0
+            wh[3] = wh[2] * 0.9
+        box = torch.cat((cxy - wh / 2, cxy + wh / 2), 1).clamp(min=0)
+        box[:, 2].clamp_(max=W)
+        box[:, 3].clamp_(max=H)
+        gt_bboxes[b, :n] = box
+        gt_labels[b, :n, 0] = torch.randint(0, nc, (n,), generator=g).float()
+        mask_gt[b, :n] = 1
+    pd_bboxes = torch.zeros(bs, A, 4)
+    for b in range(bs):
+        n = int(counts[b])
+        inside = ((anc[None, :, 0] > gt_bboxes[b, :n, None, 0]) & (anc[None, :, 1] > gt_bboxes[b, :n, None, 1])
+                  & (anc[None, :, 0] < gt_bboxes[b, :n, None, 2]) & (anc[None, :, 1] < gt_bboxes[b, :n, None, 3]))  # [n, A]
+        first = torch.where(inside.any(0), inside.float().argmax(0), torch.randint(0, n, (A,), generator=g))
+        pd_bboxes[b] = gt_bboxes[b, first] + torch.randn(A, 4, generator=g) * noise
+    pd_scores = torch.sigmoid(torch.randn(bs, A, nc, generator=g) * 2.0 - 1.0).to(score_dtype)
+    return dict(pd_scores=pd_scores, pd_bboxes=pd_bboxes, anc_points=anc, gt_labels=gt_labels, gt_bboxes=gt_bboxes, mask_gt=mask_gt)

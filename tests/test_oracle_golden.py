@@ -116,3 +116,26 @@ def test_head_tail_port_bit_exact(name):
     for i in range(3):
         assert torch.equal(raw[i], t(f"raw{i}")), f"raw level {i}"
     assert torch.equal(y, t("y"))
+
+
+def _tal_case_of(name):
+    meta = dict(golden_manifest()[name])
+    meta.pop("kind")
+    if "score_dtype" in meta:
+        meta["score_dtype"] = getattr(torch, meta["score_dtype"])
+    return rp.tal_case(**meta), meta
+
+
+@pytest.mark.parametrize("name", golden_names("tal"))
+def test_tal_assign_port_bit_exact(name):
+    """oracle/ref_port.tal_assign_port against what the unmodified TaskAlignedAssigner.forward returned on the same seeded
+    inputs (oracle/gen_golden_tal.py): all five tensors, bit for bit."""
+    g = load_golden(name)
+    c, meta = _tal_case_of(name)
+    labels, bboxes, scores, fg, gidx, ambiguous = rp.tal_assign_port(**c, num_classes=meta["nc"])
+    assert torch.equal(labels, torch.from_numpy(g["target_labels"]))
+    assert torch.equal(bboxes, torch.from_numpy(g["target_bboxes"]))
+    assert torch.equal(scores, torch.from_numpy(g["target_scores"]))
+    assert torch.equal(fg, torch.from_numpy(g["fg_mask"]))
+    assert torch.equal(gidx, torch.from_numpy(g["target_gt_idx"]))
+    assert fg.any() and (fg.sum(1) > 0).all()

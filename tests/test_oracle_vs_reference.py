@@ -85,3 +85,27 @@ def test_bbox_decode_port_equals_reference_loss_method(ref, dtype):
     (gw,) = torch.autograd.grad(want, p1, go)
     (gg,) = torch.autograd.grad(got, p2, go)
     assert torch.equal(gg, gw)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_tal_assign_port_matches_reference_assigner(seed):
+    """Fresh seeded inputs through the UNMODIFIED TaskAlignedAssigner.forward (utils/tal.py:56-178) and the port."""
+    from oracle.ref_import import load_reference
+
+    load_reference()
+    from cerberusdet.utils.tal import TaskAlignedAssigner
+
+    nc = 5 + seed % 4
+    c = rp.tal_case(seed, 2, [(24, 16), (12, 8), (6, 4)], [8, 16, 32], nc, 8 + seed % 5)
+    want = TaskAlignedAssigner(topk=10, num_classes=nc, alpha=0.5, beta=6.0)(
+        c["pd_scores"], c["pd_bboxes"], c["anc_points"], c["gt_labels"], c["gt_bboxes"], c["mask_gt"])
+    got = rp.tal_assign_port(**c, num_classes=nc)
+    for a, b in zip(got[:5], want):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+    # no boxes at all: the reference's early return (tal.py:89-93)
+    empty = {k: (v[:, :0] if k.startswith(("gt_", "mask_")) else v) for k, v in c.items()}
+    want0 = TaskAlignedAssigner(topk=10, num_classes=nc)(empty["pd_scores"], empty["pd_bboxes"], empty["anc_points"],
+                                                          empty["gt_labels"], empty["gt_bboxes"], empty["mask_gt"])
+    got0 = rp.tal_assign_port(**empty, num_classes=nc)
+    for a, b in zip(got0[:5], want0):
+        assert torch.equal(a.float(), b.float())
