@@ -93,8 +93,7 @@ __device__ __forceinline__ float align_metric(const TalParams& P, float score, f
 }
 
 __global__ void __launch_bounds__(TAL_THREADS_A) tal_topk_kernel(const __grid_constant__ TalParams P) {
-    __shared__ unsigned long long skeys[TAL_THREADS_A * TAL_MAX_TOPK];
-    __shared__ unsigned long long swarp[TAL_THREADS_A / 32];
+    __shared__ unsigned long long skeys[(TAL_THREADS_A / 32) * TAL_MAX_TOPK];
     const int b = blockIdx.x / P.G, g = blockIdx.x - b * P.G, tid = threadIdx.x;
     int* out = P.topk_idx + ((size_t)b * P.G + g) * P.topk;
     if (!(P.mask_gt[(size_t)b * P.G + g] > 0.f)) {  // padded box: the reference zeroes its topk (tal.py:146-150)
@@ -125,30 +124,48 @@ __global__ void __launch_bounds__(TAL_THREADS_A) tal_topk_kernel(const __grid_co
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < TAL_MAX_TOPK; ++i)
-        if (i < K) skeys[tid * TAL_MAX_TOPK + i] = best[i];
-    __syncthreads();
-    // K rounds of a block-wide maximum over the K * 256 surviving keys
-    unsigned long long prev = ~0ull;
+    // merge without block-wide rounds: every warp pops the K largest heads of its 32 sorted lists with shuffles (keys are
+    // unique, so exactly one lane owns each maximum and shifts its list), then warp 0 does the same over the 8 * K survivors
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned long long mine = 0ull;  // lane r ends up with the warp's r-th largest key
     for (int r = 0; r < K; ++r) {
-        unsigned long long m = 0ull;
-        for (int i = 0; i < K; ++i) {
-            const unsigned long long k = skeys[tid * TAL_MAX_TOPK + i];
-            if (k < prev && k > m) m = k;
-        }
+        unsigned long long m = best[0];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
             m = t > m ? t : m;
         }
-        if ((tid & 31) == 0) swarp[tid >> 5] = m;
-        __syncthreads();
-        m = swarp[0];
-        for (int w = 1; w < TAL_THREADS_A / 32; ++w) m = swarp[w] > m ? swarp[w] : m;
-        if (tid == 0) out[r] = m != 0ull ? (int)(~(unsigned)(m & 0xffffffffull)) : -1;
-        prev = m;
-        __syncthreads();
+        if (best[0] == m && m != 0ull) {
+#pragma unroll
+            for (int i = 0; i + 1 < TAL_MAX_TOPK; ++i) best[i] = best[i + 1];
+            best[TAL_MAX_TOPK - 1] = 0ull;
+        }
+        if (lane == r) mine = m;
+    }
+    if (lane < K) skeys[warp * TAL_MAX_TOPK + lane] = mine;
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int NW = TAL_THREADS_A / 32;
+        unsigned long long k[(NW * TAL_MAX_TOPK + 31) / 32];
+#pragma unroll
+        for (int j = 0; j < (NW * TAL_MAX_TOPK + 31) / 32; ++j) {
+            const int idx = lane + 32 * j, w = idx / TAL_MAX_TOPK, i = idx - w * TAL_MAX_TOPK;
+            k[j] = (w < NW && i < K) ? skeys[idx] : 0ull;
+        }
+        for (int r = 0; r < K; ++r) {
+            unsigned long long m = 0ull;
+#pragma unroll
+            for (int j = 0; j < (NW * TAL_MAX_TOPK + 31) / 32; ++j) m = k[j] > m ? k[j] : m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+                m = t > m ? t : m;
+            }
+#pragma unroll
+            for (int j = 0; j < (NW * TAL_MAX_TOPK + 31) / 32; ++j)
+                if (k[j] == m) k[j] = 0ull;
+            if (lane == 0) out[r] = m != 0ull ? (int)(~(unsigned)(m & 0xffffffffull)) : -1;
+        }
     }
 }
 
@@ -220,21 +237,21 @@ __global__ void __launch_bounds__(TAL_THREADS_B) tal_assign_kernel(const __grid_
 }
 
 // target_scores [B, A, C] = one_hot(label) * fg * norm (tal.py:174-177, :107-108): the one big output (43 MB at B=64,
-// A=8400, C=20), written by the whole GPU -- one thread per anchor walks its C entries
+// A=8400, C=20), written by the whole GPU with consecutive threads on consecutive elements
 __global__ void __launch_bounds__(256) tal_scores_kernel(const __grid_constant__ TalParams P) {
-    const size_t n = (size_t)P.B * P.A;
-    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(o / P.A);
-        int label = -1;
+    const size_t n = (size_t)P.B * P.A * P.C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t o = i / P.C;  // (image, anchor)
+        const int c = (int)(i - o * P.C);
         float v = 0.f;
         if (P.cnt[o] > 0) {
-            const int g = P.gsel[o];
-            label = (int)P.gt_labels[(size_t)b * P.G + g];
-            const float* ps = P.pos + ((size_t)b * P.G + g) * 2;
-            v = __fdiv_rn(__fmul_rn(P.aval[o], ps[1]), __fadd_rn(ps[0], P.eps));
+            const int b = (int)(o / P.A), g = P.gsel[o];
+            if ((int)P.gt_labels[(size_t)b * P.G + g] == c) {
+                const float* ps = P.pos + ((size_t)b * P.G + g) * 2;
+                v = __fdiv_rn(__fmul_rn(P.aval[o], ps[1]), __fadd_rn(ps[0], P.eps));
+            }
         }
-        float* ts = P.target_scores + o * P.C;
-        for (int c = 0; c < P.C; ++c) ts[c] = c == label ? v : 0.f;
+        P.target_scores[i] = v;
     }
 }
 
@@ -285,8 +302,8 @@ extern "C" int cerb_tal_assign(const void* pd_scores, const float* pd_bboxes, co
     P.target_gt_idx = target_gt_idx;
     tal_topk_kernel<<<B * G, TAL_THREADS_A, 0, (cudaStream_t)stream>>>(P);
     tal_assign_kernel<<<B, TAL_THREADS_B, 0, (cudaStream_t)stream>>>(P);
-    const size_t n_rows = (size_t)B * A;
-    const int blocks = (int)((n_rows + 255) / 256 < 148 * 8 ? (n_rows + 255) / 256 : 148 * 8);
+    const size_t n_out = (size_t)B * A * C;
+    const int blocks = (int)((n_out + 255) / 256 < 148 * 16 ? (n_out + 255) / 256 : 148 * 16);
     tal_scores_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
