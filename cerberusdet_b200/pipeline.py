@@ -27,7 +27,6 @@ from . import ops
 # on a third branch of the step graph; "after" = small graphs replayed after the step graph; "off" = never (nothing is
 # delivered: timing experiments only)
 _SIDE = os.environ.get("CERB_SIDE", "piggyback")
-_DUMMY3 = os.environ.get("CERB_DUMMY3", "0") == "1"
 # how the two kernels of an overlapped step are made concurrent: "pdl" = ONE stream, NMS(k-1) then decode(k) launched with
 # the programmatic-serialization attribute (its CTAs are dispatched as soon as every NMS CTA is running, never before: the
 # NMS CTAs, 109 KB of shared memory each, must be placed first or they wait for decode CTAs to drain); "streams" = two
@@ -73,7 +72,6 @@ class PostHeadPipeline:
         with torch.cuda.device(self.device):
             self.ybuf = [ops.decode_buffers(self.heads) for _ in range(2)]
             self.sa, self.sb, self.sc = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-            self._dummy = torch.zeros(1, device=self.device)
             # eager warm-up of both kernels (module load, function attributes) before anything is captured
             ys = ops.decode_heads(self.heads, self.strides, out=self.ybuf[0])
             ops.nms_batched(ys, out=self.outs[0], **self.kw)
@@ -177,12 +175,8 @@ class PostHeadPipeline:
                         if standalone and _SIDE == "last3":
                             with torch.cuda.stream(self.sc):
                                 side_kernel()
-                        if _DUMMY3 and not standalone:  # tools/ experiment: an (almost) empty third branch, created last
-                            self.sc.wait_stream(self.sa)
-                            with torch.cuda.stream(self.sc):
-                                self._dummy.add_(1)
                         self.sa.wait_stream(self.sb)
-                        if (standalone and _SIDE in ("branch3", "last3")) or (_DUMMY3 and not standalone):
+                        if standalone and _SIDE in ("branch3", "last3"):
                             self.sa.wait_stream(self.sc)
                     elif dec is not None:
                         self._decode(dec)
@@ -196,9 +190,9 @@ class PostHeadPipeline:
 
     def _capture_timed(self, p: int, side: bool = False):
         """Instrumented step: the same two launches as a normal step (decode of this batch, NMS of the previous one) in
-        SERIAL order with timing events recorded by graph nodes:  E0 ; decode ; {E1 on a side branch} ; NMS ; E2.
-        E1 hangs off the decode kernel on a second stream, so the NMS kernel keeps its programmatic (early-launch) edge
-        to the decode kernel; E0..E1 is the decode kernel alone on the GPU, E1..E2 the NMS kernel."""
+        SERIAL order with timing events recorded by graph nodes on the launching stream:  E0 ; decode ; E1 ; NMS ; E2.
+        E0..E1 is the decode kernel alone on the GPU, E1..E2 the NMS kernel (without its programmatic early launch: the
+        event node sits between the two kernels)."""
         ev = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(3)]
         g = torch.cuda.CUDAGraph()
         self.sa.wait_stream(torch.cuda.current_stream(self.device))
@@ -206,11 +200,9 @@ class PostHeadPipeline:
             with torch.cuda.graph(g, stream=self.sa):
                 ev[0].record(self.sa)
                 self._decode(p)
-                self.sb.wait_stream(self.sa)
-                ev[1].record(self.sb)
+                ev[1].record(self.sa)
                 self._nms(1 - p, side)  # (side: the launch carries this rank's delivery work, as in the steady-state graph)
                 ev[2].record(self.sa)
-                self.sa.wait_stream(self.sb)
         torch.cuda.current_stream(self.device).wait_stream(self.sa)
         return g, ev
 

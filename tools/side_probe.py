@@ -104,10 +104,10 @@ def main():
     if args.one:
         ms, ok = run(args.steps, args.one)
         print(json.dumps({"mode": args.one, "side": os.environ.get("CERB_SIDE", "branch"), "push_mode": os.environ.get("CERB_DEBUG_PUSH_MODE"),
-                          "push_ctas": os.environ.get("CERB_DEBUG_PUSH_CTAS"), "dummy3": os.environ.get("CERB_DUMMY3"), "ms_per_step": round(ms, 5), "delivered": ok}))
+                          "push_ctas": os.environ.get("CERB_DEBUG_PUSH_CTAS"), "schedule": os.environ.get("CERB_SCHEDULE", "pdl"), "ms_per_step": round(ms, 5), "delivered": ok}))
         return
     # (a collect without a matching flag-setting push would sit out its 2 s bound every step: never combine those)
-    if os.environ.get("SIDE_PROBE_SET", "placement") == "dummy":  # does a third branch help even without a delivery?  (bimodal step times)
+    if os.environ.get("SIDE_PROBE_SET", "placement") == "dummy":  # is it buffer placement, the packed outputs, or the side kernel?  (bimodal step times)
         runs = (("none", {}), ("none_pad", {}), ("none_outs", {}), ("full", {"CERB_SIDE": "last3"}), ("full", {"CERB_SIDE": "last3", "CERB_DEBUG_PUSH_MODE": "2"})) * 2
     elif os.environ.get("SIDE_PROBE_SET", "placement") == "placement":  # where in the step graph does the side kernel hurt least?
         runs = (("none", {}),) + tuple(("full", {"CERB_SIDE": v}) for v in ("branch3", "last3", "pre_nms", "post_nms", "post_decode")) + (("none", {}),)
