@@ -190,9 +190,11 @@ class PostHeadPipeline:
 
     def _capture_timed(self, p: int, side: bool = False):
         """Instrumented step: the same two launches as a normal step (decode of this batch, NMS of the previous one) in
-        SERIAL order with timing events recorded by graph nodes on the launching stream:  E0 ; decode ; E1 ; NMS ; E2.
-        E0..E1 is the decode kernel alone on the GPU, E1..E2 the NMS kernel (without its programmatic early launch: the
-        event node sits between the two kernels)."""
+        SERIAL order with timing events recorded by graph nodes:  E0 ; decode ; {E1 on a side branch} ; NMS ; E2.
+        E1 hangs off the decode kernel on a second stream (which waits for the launching stream first), so the NMS kernel
+        keeps its programmatic (early-launch) edge to the decode kernel; E0..E1 is the decode kernel alone on the GPU,
+        E1..E2 the NMS kernel.  (With E1 on the launching stream itself the decode reads 1 us shorter and the NMS 5.5 us
+        longer -- it loses the early launch -- which costs the driver's 20-step run 3 % of its value: gpurun_out/call_v3.)"""
         ev = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(3)]
         g = torch.cuda.CUDAGraph()
         self.sa.wait_stream(torch.cuda.current_stream(self.device))
@@ -200,9 +202,11 @@ class PostHeadPipeline:
             with torch.cuda.graph(g, stream=self.sa):
                 ev[0].record(self.sa)
                 self._decode(p)
-                ev[1].record(self.sa)
+                self.sb.wait_stream(self.sa)
+                ev[1].record(self.sb)
                 self._nms(1 - p, side)  # (side: the launch carries this rank's delivery work, as in the steady-state graph)
                 ev[2].record(self.sa)
+                self.sa.wait_stream(self.sb)
         torch.cuda.current_stream(self.device).wait_stream(self.sa)
         return g, ev
 
