@@ -554,6 +554,26 @@ def main():
         per_rank = [[round(float(v), 5) for v in t.tolist()] for t in allr]  # [elapsed ms, decode ms, NMS ms] of every rank
         elapsed_ms = max(r[0] for r in per_rank)
 
+    # ---- the same engine without the instrumented steps (outside the timed region, reported beside `value`): what K steps
+    # cost when none of them is serialised for the roofline brackets -- the steady state of a long stream of batches
+    steady = None
+    if not args.serial:
+        ss_steps = 200
+        run_steps(10)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        run_steps(ss_steps)
+        s1.record()
+        barrier()
+        ss_ms = s0.elapsed_time(s1)
+        if world > 1:
+            tt = torch.tensor([ss_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ss_ms = float(tt.item())
+        steady = {"steps": ss_steps, "ms_per_step": ss_ms / ss_steps, "value": B_PER_GPU * world * ss_steps / (ss_ms * 1e-3), "unit": "images/s",
+                  "what": "the timed region's loop without instrumented steps (every step overlapped), max over ranks; not the headline"}
+
     # ---- end to end through the host-buffer API (pinned host in, pinned host out)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -645,6 +665,9 @@ def main():
                                                                         "beside it (griddepcontrol / programmatic stream serialization)")
         line["clocks"] = clk.summary()
         line["equality"] = equality
+        if steady is not None:
+            line["steady_state"] = steady
+            line["instrumented_steps"] = len(dec_ms)
         if per_rank is not None:
             line["per_rank_ms"] = {"elapsed": [r[0] for r in per_rank], "decode_instrumented": [r[1] for r in per_rank],
                                    "nms_instrumented": [r[2] for r in per_rank]}
