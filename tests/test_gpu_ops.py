@@ -95,12 +95,15 @@ def test_decode_out_buffers_and_inference_mode():
         ops.decode_heads(heads, STRIDES, out=buf[:-1])
 
 
-@pytest.mark.parametrize("overlap", [True, False])
-def test_pipeline_equals_direct_calls(overlap):
-    """The streaming engine (static buffers, CUDA graphs; decode of batch k overlapped with the NMS of batch k-1) gives
-    the bits of the plain two-call path, batch after batch, also when the static inputs change between steps."""
-    from cerberusdet_b200 import ops
+@pytest.mark.parametrize("overlap,schedule", [(True, "pdl"), (True, "streams"), (False, "pdl")])
+def test_pipeline_equals_direct_calls(overlap, schedule, monkeypatch):
+    """The streaming engine (static buffers, CUDA graphs; decode of batch k beside the NMS of batch k-1 -- on one stream
+    with a programmatic launch, or on two graph branches) gives the bits of the plain two-call path, batch after batch,
+    also when the static inputs change between steps."""
+    from cerberusdet_b200 import ops, pipeline
     from cerberusdet_b200.pipeline import PostHeadPipeline
+
+    monkeypatch.setattr(pipeline, "_SCHEDULE", schedule)
 
     batches = [_heads(bsz=4, cfg=70 + i) for i in range(4)]
     static = [[x.clone() for x in lv] for lv in batches[0]]
