@@ -414,6 +414,12 @@ static int nms_impl(const void* const* pred, const int* nc, int T, int B, int A,
         P.push_src = (const float*)dv->push_src;
         P.push_dst = (float*)dv->push_dst;
         P.push_words = (unsigned)dv->push_words;
+        if (dv->push_src != nullptr) {  // <= 16 sweeps of 8 KB per delivery CTA, at most 16 CTAs (they take NMS-sized slots)
+            size_t n = (dv->push_words / 4 + 512 * 16 - 1) / (512 * 16);
+            P.deliver_ctas = (int)(n < 1 ? 1 : (n > 16 ? 16 : n));
+        } else if (dv->collect_flags != nullptr) {
+            P.deliver_ctas = 1;
+        }
         if (dv->collect_flags != nullptr) {
             P.col_flags = (const unsigned*)dv->collect_flags;
             for (int r = 0; r < dv->world; ++r) P.col_ack[r] = (unsigned*)dv->collect_ack[r];

@@ -71,6 +71,7 @@ struct NmsParams {
     const float* push_src;         // local staging of the previous batch (16-byte aligned), null = direct form
     float* push_dst;               // dst's slot (peer-mapped)
     unsigned push_words;           // multiple of 4
+    int deliver_ctas;              // host only -> kernel: extra CTAs of the launch that do the delivery (0 = none)
     // rank dst: CTA 0 takes the batch the other ranks pushed during the previous step (cerb_deliver_collect's job)
     const unsigned* col_flags;     // local [world], null = off
     unsigned* col_ack[16];         // peer-mapped

@@ -704,36 +704,56 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
 
-    BLOCK_T_START
     // a kernel launched behind this one with the programmatic attribute (the NEXT batch's decode in the single-stream
     // overlapped schedule) may start as soon as every CTA of this grid is running
     asm volatile("griddepcontrol.launch_dependents;");
-    if (P.push_src != nullptr) {
-        // piggyback delivery: push the PREVIOUS batch (complete in local staging since the previous launch) into rank
-        // dst's slot before anything else; the fences that publish it are at the very end of this kernel, by when
-        // these stores have long landed.  dst must have taken the batch that was in the slot (never spins in steady
-        // state; bounded -- a lost peer must not hang the GPU).
-        if (threadIdx.x == 0) {
-            const unsigned need = *reinterpret_cast<volatile unsigned*>(P.deliver_seq);
-            for (unsigned spins = 0; ld_relaxed_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+    if ((int)blockIdx.x >= P.T * P.B) {
+        // The launch's extra CTAs (only present with a piggyback delivery descriptor): this rank's side of the delivery of
+        // an earlier batch, beside the segment CTAs and on nobody's critical path.
+        const int d = (int)blockIdx.x - P.T * P.B;  // 0 .. P.deliver_ctas - 1
+        if (P.push_src != nullptr) {
+            // writer: push the PREVIOUS batch (complete in local staging since the previous launch) into rank dst's slot
+            // with 128-bit stores, then publish the slot's new batch count in dst's flag word: every delivery CTA orders
+            // its stores before its count at GPU scope, the last one releases at system scope (the NVLink round trips
+            // of the fences are paid by these CTAs only, ~10 us into a ~50 us kernel).  dst must have taken the batch
+            // that was in the slot (never spins in steady state; bounded: a lost peer must not hang the GPU).
+            if (threadIdx.x == 0) {
+                const unsigned need = *reinterpret_cast<volatile unsigned*>(P.deliver_seq);
+                for (unsigned spins = 0; ld_relaxed_sys(P.deliver_ack) < need && spins < 8000000u; ++spins) __nanosleep(256);
+            }
+            __syncthreads();
+            const float4* __restrict__ src = reinterpret_cast<const float4*>(P.push_src);
+            float4* __restrict__ dst4 = reinterpret_cast<float4*>(P.push_dst);
+            for (unsigned i = (unsigned)d * NMS_THREADS + threadIdx.x; i < P.push_words / 4; i += (unsigned)P.deliver_ctas * NMS_THREADS)
+                dst4[i] = src[i];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                if (atomicAdd(P.deliver_done, 1u) == (unsigned)P.deliver_ctas - 1u) {
+                    __threadfence();
+                    *reinterpret_cast<volatile unsigned*>(P.deliver_done) = 0u;
+                    const unsigned n = *reinterpret_cast<volatile unsigned*>(P.deliver_seq) + 1u;
+                    *reinterpret_cast<volatile unsigned*>(P.deliver_seq) = n;
+                    st_release_sys(P.deliver_flag, n);
+                }
+            }
         }
-        __syncthreads();
-        const float4* __restrict__ src = reinterpret_cast<const float4*>(P.push_src);
-        float4* __restrict__ dst4 = reinterpret_cast<float4*>(P.push_dst);
-        for (unsigned i = blockIdx.x * NMS_THREADS + threadIdx.x; i < P.push_words / 4; i += gridDim.x * NMS_THREADS) dst4[i] = src[i];
-    }
-    if (P.col_flags != nullptr && blockIdx.x == 0) {
-        // rank dst: take the batch the other ranks pushed during the previous step and acknowledge it (one thread per rank)
-        const int r = threadIdx.x;
-        const unsigned need = *reinterpret_cast<volatile unsigned*>(P.col_collected) + 1u;
-        if (r < P.col_world && r != P.col_dst) {
-            for (unsigned spins = 0; ld_relaxed_sys(P.col_flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
-            (void)ld_acquire_sys(P.col_flags + r);
-            st_release_sys(P.col_ack[r], need);
+        if (P.col_flags != nullptr && d == 0) {
+            // rank dst: take the batch the other ranks pushed during the previous step and acknowledge it (one thread per
+            // rank); a late writer delays this CTA only
+            const int r = threadIdx.x;
+            const unsigned need = *reinterpret_cast<volatile unsigned*>(P.col_collected) + 1u;
+            if (r < P.col_world && r != P.col_dst) {
+                for (unsigned spins = 0; ld_relaxed_sys(P.col_flags + r) < need && spins < 8000000u; ++spins) __nanosleep(256);
+                (void)ld_acquire_sys(P.col_flags + r);
+                st_release_sys(P.col_ack[r], need);
+            }
+            __syncthreads();
+            if (r == 0) *reinterpret_cast<volatile unsigned*>(P.col_collected) = need;
         }
-        __syncthreads();
-        if (r == 0) *reinterpret_cast<volatile unsigned*>(P.col_collected) = need;
+        return;
     }
+    BLOCK_T_START
     const int seg = blockIdx.x;
     const int task = seg / P.B, b = seg - task * P.B;
     const int nc = P.nc[task], A = P.A;
@@ -1157,8 +1177,8 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
     }
     // rows past the count are zero so the padded [T, B, max_det, 6] output is deterministic without a separate fill
     for (int i = kept * 6 + tid; i < max_det * 6; i += NMS_THREADS) dets[i] = 0.f;
-    if (P.deliver_flag != nullptr) {
-        // tell rank dst that this rank's batch is complete.  Every CTA orders its stores before its count at GPU scope
+    if (P.deliver_flag != nullptr && P.push_src == nullptr) {
+        // direct form: tell rank dst that this rank's batch is complete.  Every CTA orders its stores before its count at GPU scope
         // (fence + atomic = release; the per-CTA fence is the cheap one); the last CTA -- which has observed every count
         // (acquire at GPU scope) -- fences ONCE at system scope and releases the slot's new sequence number into dst's
         // flag.  PTX causality order is transitive across the two scopes, so a reader on dst that acquires the flag sees
@@ -1166,7 +1186,7 @@ __global__ void __launch_bounds__(NMS_THREADS, MINB) nms_kernel(const __grid_con
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            if (atomicAdd(P.deliver_done, 1u) == gridDim.x - 1) {
+            if (atomicAdd(P.deliver_done, 1u) == (unsigned)(P.T * P.B) - 1u) {
                 __threadfence();
                 *reinterpret_cast<volatile unsigned*>(P.deliver_done) = 0u;
                 const unsigned n = *reinterpret_cast<volatile unsigned*>(P.deliver_seq) + 1u;
@@ -1248,7 +1268,8 @@ template <typename T, bool MULTI, int MINB> static cudaError_t launch_nms_t(cons
     // it has completed -- hides the launch latency and the prologue behind the decode kernel's tail
     const bool pdl = P.pdl != 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(P.T * P.B));
+    // (+ the delivery CTAs of the piggyback form, see the top of the kernel)
+    cfg.gridDim = dim3((unsigned)(P.T * P.B) + (unsigned)P.deliver_ctas);
     cfg.blockDim = dim3(NMS_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;

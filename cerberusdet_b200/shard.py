@@ -162,9 +162,8 @@ class PeerDelivery:
         stores the acknowledgement into rank r's ``ack[slot]``.
 
     The NMS kernel writes LOCAL memory exactly as on one GPU.  In steady state neither side is a kernel of its own: the
-    NEXT NMS launch carries them (``nms_deliver_args(slot, piggyback=True)`` -> ``cerb_nms_deliver``): a writer's launch
-    pushes the previous batch at its start and publishes the flag at its end, ~50 us later, when the stores have long
-    landed; CTA 0 of dst's launch does the collect.  The step graph keeps the shape it has on one GPU (a third graph
+    NEXT NMS launch carries them (``nms_deliver_args(slot, piggyback=True)`` -> ``cerb_nms_deliver``) in a few extra CTAs
+    beside its segment CTAs: a writer's push the previous batch and publish the flag, one on dst does the collect.  The step graph keeps the shape it has on one GPU (a third graph
     branch, however small its kernel, costs the decode / NMS overlap: +13 us per step, profiles/r02_multi_gpu.md), the
     NVLink round trips of the fences are on nobody's critical path, and a step stays one graph replay on every rank.
     ``push`` / ``collect`` as stand-alone kernels serve the first and last batches of a run.  No NCCL kernel takes SMs

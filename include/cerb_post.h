@@ -161,12 +161,13 @@ int cerb_nms_stats(const void* const* pred, const int* nc, int T, int B, int A, 
  * data path.  Three forms:
  *
  * cerb_nms_deliver, piggyback (push_src != NULL; what shard.PeerDelivery uses): cerb_nms writing LOCAL `dets` / `counts`
- *   as on one GPU; at its START the launch pushes the PREVIOUS batch's packed words (dets rows then counts, left in
- *   local staging by the previous launch: push_src -> push_dst, push_words 32-bit words, a multiple of 4, both
- *   16-byte aligned) with 128-bit stores, and publishes that slot's flag at its END, ~50 us later, when the stores have
- *   long landed: the fences cost nothing and the step graph has no extra node.  On rank dst (collect_flags != NULL)
- *   CTA 0 also takes the batch the writers pushed during the previous step: thread r waits for collect_flags[r] to
- *   exceed *collect_count and stores the acknowledgement into collect_ack[r] (rank r's ack word, peer-mapped).
+ *   as on one GPU; the launch gets up to 16 EXTRA CTAs that push the PREVIOUS batch's packed words (dets rows then
+ *   counts, left in local staging by the previous launch: push_src -> push_dst, push_words 32-bit words, a multiple of
+ *   4, both 16-byte aligned) with 128-bit stores and publish that slot's flag when they are done.  They run beside the
+ *   segment CTAs, so the NVLink round trips of their fences are on nobody's critical path, and the step graph has no
+ *   extra node.  On rank dst (collect_flags != NULL) one extra CTA takes the batch the writers pushed during the
+ *   previous step: thread r waits for collect_flags[r] to exceed *collect_count and stores the acknowledgement into
+ *   collect_ack[r] (rank r's ack word, peer-mapped).
  * cerb_nms_deliver, direct (push_src == NULL, flag_remote != NULL): `dets` / `counts` ARE dst's slot; rows cross NVLink
  *   one by one and the fences sit at the end of the NMS kernel (+7 us per step at N=2).
  * cerb_deliver_push / cerb_deliver_collect: the two sides as kernels of their own (the last batches of a run, and
