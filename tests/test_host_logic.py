@@ -397,3 +397,82 @@ def test_batched_rescale_equals_reference_scale_boxes_on_cpu():
             want = boxes[i].clone()
             scale_boxes((384, 640), want, ori[i], ratio_pad=rp[i])
             assert torch.equal(got[i], want)
+
+
+@pytest.mark.parametrize("role", ["writer", "dst"])
+@pytest.mark.parametrize("side", ["piggyback", "branch3", "after"])
+def test_pipeline_delivery_bookkeeping(role, side, monkeypatch):
+    """Which batch is pushed / collected at which step (pipeline.PostHeadPipeline.step / flush with an in-graph delivery),
+    without a GPU: the graphs are replaced by recorders.  For every run length, on both sides of the delivery: every batch
+    is pushed (collected) exactly once, in order, into the slot of its parity; a batch is pushed no earlier than the step
+    after its NMS launch and before the NMS launch that overwrites its staging slot; it is collected no earlier than one
+    step after it was pushed; instrumented steps and the stand-alone placements change none of that."""
+    from types import SimpleNamespace
+
+    from cerberusdet_b200 import pipeline
+
+    monkeypatch.setattr(pipeline, "_SIDE", side)
+    log = []
+
+    class G:
+        def __init__(self, what, slot=None):
+            self.what, self.slot = what, slot
+
+        def replay(self):
+            log.append((self.what, self.slot, pipe.k))
+
+    def make(n_steps, timed_at):
+        p = object.__new__(pipeline.PostHeadPipeline)
+        p.overlap, p.k, p.pending = True, 0, None
+        p.delivery = SimpleNamespace(rank=1 if role == "writer" else 0, dst=0, direct=False)
+        p._g_first = [G("first", s) for s in (0, 1)]
+        p._g_step = [G("plain", s) for s in (0, 1)]
+        p._g_full = [G("full", s) for s in (0, 1)]
+        p._g_flush = [G("flush", s) for s in (0, 1)]
+        p._g_flush_full = [G("flush_full", s) for s in (0, 1)]
+        p._g_push = [G("push", s) if role == "writer" else None for s in (0, 1)]
+        p._g_collect = [G("collect", s) if role == "dst" else None for s in (0, 1)]
+        p.timed = [(G("timed_side" if (k >= 3 and side == "piggyback") else "timed", k & 1), None) for k in timed_at]
+        p.timed_parity = [k & 1 for k in timed_at]
+        p.timed_has_side = [k >= 3 and side == "piggyback" for k in timed_at]
+        return p
+
+    for n_steps in (1, 2, 3, 4, 5, 8, 9):
+        for timed_at in ([], [1], [2, 3], [1, 2, 3, 4, 5, 6, 7]):
+            timed_at = [k for k in timed_at if k < n_steps]
+            log.clear()
+            pipe = make(n_steps, timed_at)
+            slot_of = {k: i for i, k in enumerate(timed_at)}
+            for k in range(n_steps):
+                pipe.step(timed=slot_of.get(k))
+            pipe.flush()
+            # expand the log into delivery events (batch, at_step); a graph that carries the side work does it for batch
+            # k-2 (push) / k-3 (collect) of the step k it belongs to; the flush's launch is NMS launch n-1 = "step n"
+            events = []
+            in_flush = False
+            for what, slot, k_after in log:
+                in_flush = in_flush or what in ("flush", "flush_full")
+                k = n_steps if in_flush else k_after - 1  # (step() has already advanced the counter when it replays)
+                if what in ("full", "timed_side", "flush_full"):
+                    step = k if what != "flush_full" else n_steps
+                    batch = step - 2 if role == "writer" else step - 3
+                    assert batch >= 0 and slot == (step & 1 if what != "flush_full" else (n_steps - 1) & 1)
+                    events.append((batch, step))
+                elif what in ("push", "collect"):
+                    events.append((None, k, slot))
+            # stand-alone kernels are logged with their slot only: recover their batch from the order
+            batches, nxt = [], 0
+            for e in events:
+                if e[0] is None:
+                    assert e[2] == nxt & 1, f"{role} {side} n={n_steps} timed={timed_at}: slot {e[2]} for batch {nxt}"
+                    batches.append((nxt, e[1]))
+                else:
+                    assert e[0] == nxt, f"{role} {side} n={n_steps} timed={timed_at}: batch {e[0]} where {nxt} was due"
+                    batches.append(e)
+                nxt += 1
+            assert [b for b, _ in batches] == list(range(n_steps)), f"{role} {side} n={n_steps} timed={timed_at}: {batches}"
+            for b, at in batches:
+                if role == "writer":  # beside step b+2 (its NMS launch was step b+1; launch b+2, at step b+3, reuses the staging) or in the flush
+                    assert at == b + 2 or (at == n_steps and b >= n_steps - 2), (b, at, n_steps)
+                else:                 # one step after the writers pushed it, or in the flush
+                    assert at == b + 3 or (at == n_steps and b >= n_steps - 3), (b, at, n_steps)
