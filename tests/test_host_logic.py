@@ -67,6 +67,38 @@ def test_argument_validation_without_gpu():
     rc = lib.cerb_decode_split(_lib.ptr_array([0]), None, _lib.int_array([5]), 1, 1, 1, _lib.int_array([2]), _lib.int_array([2]),
                                _lib.float_array([8.0]), 0, _lib.ptr_array([0]), None, None, None)
     assert rc == _lib.CERB_EINVAL and b"null" in lib.cerb_last_error()
+    # round-2 entry points: head-tail fusion, delivery, TAL assigner
+    one = _lib.ptr_array([256])
+    ia = _lib.int_array
+    rc = lib.cerb_head_tail(one, one, one, one, one, one, ia([64]), ia([64]), ia([4]), 1, 1, 1, ia([8]), ia([8]), _lib.float_array([8.0]),
+                            _lib.CERB_F32, one, None, None, None)
+    assert rc == _lib.CERB_EINVAL and b"fp16 only" in lib.cerb_last_error()
+    rc = lib.cerb_head_tail(one, one, one, one, one, one, ia([64]), ia([64]), ia([4]), 1, 1, 0, ia([8]), ia([8]), _lib.float_array([8.0]),
+                            _lib.CERB_F16, one, None, None, None)
+    assert rc == _lib.CERB_EINVAL and b"B=0" in lib.cerb_last_error()
+    rc = lib.cerb_deliver_push(fake, ctypes.c_void_p(260), 64, fake, fake, fake, fake, None)
+    assert rc == _lib.CERB_EINVAL and b"16-byte" in lib.cerb_last_error()
+    rc = lib.cerb_deliver_push(fake, fake, 62, fake, fake, fake, fake, None)
+    assert rc == _lib.CERB_EINVAL and b"multiple of 4" in lib.cerb_last_error()
+    rc = lib.cerb_deliver_collect(fake, _lib.ptr_array([None, 256]), fake, 17, 0, None)
+    assert rc == _lib.CERB_EINVAL and b"at most 16 ranks" in lib.cerb_last_error()
+    rc = lib.cerb_deliver_collect(fake, _lib.ptr_array([None, None]), fake, 2, 0, None)
+    assert rc == _lib.CERB_EINVAL and b"ack_remote[1]" in lib.cerb_last_error()
+    dv = _lib.Delivery()
+    dv.push_src, dv.push_dst, dv.push_words = 256, 512, 64  # a push without protocol words
+    rc = lib.cerb_nms_deliver(_lib.ptr_array([256]), ia([5]), 1, 1, 16, 0, 0.25, 0.45, None, 0, 0, 0, 300, 30000, 7680.0, None, fake, fake,
+                              None, 0, ctypes.byref(dv), None)
+    assert rc == _lib.CERB_EINVAL and b"protocol words" in lib.cerb_last_error()
+    rc = lib.cerb_nms_deliver(_lib.ptr_array([256]), ia([5]), 1, 1, 16, 0, 0.25, 0.45, None, 0, 0, 0, 300, 30000, 7680.0, None, fake, fake,
+                              None, 0, None, None)
+    assert rc == _lib.CERB_EINVAL and b"null delivery" in lib.cerb_last_error()
+    assert lib.cerb_tal_workspace_bytes(64, 8400, 20, 10) == (64 * 20 * 10 + 64 * 8400 * 3 + 64 * 20 * 2) * 4
+    rc = lib.cerb_tal_assign(fake, fake, fake, fake, fake, fake, 2, 100, 5, 0, 10, 0.5, 6.0, 1e-9, 1, fake, fake, fake, fake, fake, fake, 1 << 20, None)
+    assert rc == _lib.CERB_EINVAL and b"G=0" in lib.cerb_last_error()
+    rc = lib.cerb_tal_assign(fake, fake, fake, fake, fake, fake, 2, 100, 5, 3, 17, 0.5, 6.0, 1e-9, 1, fake, fake, fake, fake, fake, fake, 1 << 20, None)
+    assert rc == _lib.CERB_EINVAL and b"topk=17" in lib.cerb_last_error()
+    rc = lib.cerb_tal_assign(fake, fake, fake, fake, fake, fake, 2, 100, 5, 3, 10, 0.5, 6.0, 1e-9, 1, fake, fake, fake, fake, fake, fake, 16, None)
+    assert rc == _lib.CERB_ENOSPC and b"workspace" in lib.cerb_last_error()
 
 
 def test_ops_refuse_cpu_tensors():
