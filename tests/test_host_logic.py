@@ -508,3 +508,28 @@ def test_pipeline_delivery_bookkeeping(role, side, monkeypatch):
                     assert at == b + 2 or (at == n_steps and b >= n_steps - 2), (b, at, n_steps)
                 else:                 # one step after the writers pushed it, or in the flush
                     assert at == b + 3 or (at == n_steps and b >= n_steps - 3), (b, at, n_steps)
+
+
+@pytest.mark.skipif(not REF, reason="needs the reference tree (/root/reference or oracle/_ref)")
+def test_can_fuse_tail_preconditions_on_the_real_detect():
+    """detect.can_fuse_tail mirrors cerb_head_tail's preconditions on the reference's own Detect module (no GPU needed):
+    half tensors, both towers ending in a biased 1x1 nn.Conv2d with a multiple-of-16 input width, every H*W a multiple of
+    8, nc <= 192 -- and FusedHeads hands out exactly the last convolutions' parameters."""
+    from oracle.ref_import import load_reference
+
+    ref = load_reference()
+    from cerberusdet_b200 import detect
+
+    head = ref.yolo.Detect(nc=20, ch=(64, 128, 256)).half()
+    x640 = [torch.zeros(1, c, 80 >> i, 80 >> i, dtype=torch.float16) for i, c in enumerate((64, 128, 256))]
+    assert detect.can_fuse_tail(head, x640)
+    assert not detect.can_fuse_tail(head, [t.float() for t in x640])                       # fp32 activations
+    x320 = [torch.zeros(1, c, 40 >> i, 40 >> i, dtype=torch.float16) for i, c in enumerate((64, 128, 256))]
+    assert not detect.can_fuse_tail(head, x320)                                           # P5 is 10x10: H*W % 8 != 0
+    assert not detect.can_fuse_tail(ref.yolo.Detect(nc=20, ch=(64, 128, 256)), x640)      # fp32 weights
+    wide = ref.yolo.Detect(nc=365, ch=(64, 128, 256)).half()
+    assert not detect.can_fuse_tail(wide, x640)                                           # nc > 192
+    fused = detect.FusedHeads([t for t in x640], [t for t in x640], head)
+    bw, bb, cw, cb = fused.weights()
+    assert bw[0] is head.cv2[0][-1].weight and cb[2] is head.cv3[2][-1].bias and tuple(cw[1].shape) == (20, head.cv3[1][-1].in_channels, 1, 1)
+    assert tuple(bw[0].shape)[0] == 64 and head.cv2[0][-1].in_channels % 16 == 0
