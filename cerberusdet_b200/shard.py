@@ -1,11 +1,13 @@
-"""Image sharding across the GPUs of one box and the single collective of the path.
+"""Image sharding across the GPUs of one box and the single exchange of the path.
 
 Every (image, task) segment is independent in decode and NMS (reference
 utils/general.py:424 loops over images; tasks are separate calls at
 cerberusdet_inference.py:125-135), so a batch shards by image with no data-path
-collective.  The only exchange is one gather of the padded detections
-``[T, B_loc, max_det, 6]`` + counts ``[T, B_loc]`` to rank 0 (NCCL over NVLink on
-GPUs; gloo in the CPU tests).
+collective.  The only exchange is that the padded detections
+``[T, B_loc, max_det, 6]`` + counts ``[T, B_loc]`` of every rank reach rank 0: through
+peer-mapped memory over NVLink with a flag / acknowledge hand-shake the kernels run
+themselves (``PeerDelivery``), or one ``dist.gather`` per batch (``GatherDelivery``:
+NCCL fallback, gloo in the CPU tests).
 """
 from __future__ import annotations
 
